@@ -1,0 +1,258 @@
+/*
+ * ptlflow_b200 -- C ABI of the B200-native RAFT-family inference hot path.
+ *
+ * This is the drop-in boundary: a plain C interface (device pointers, sizes, a CUDA
+ * stream) that replaces, for the RAFT hot path, what the reference reaches through
+ *   - its native plugin `alt_cuda_corr`      ptlflow/utils/external/alt_cuda_corr/correlation.cpp:23-54
+ *   - the corr-block protocol                ptlflow/models/raft/corr.py:13-118
+ *   - the update block / upsampling modules  ptlflow/models/raft/update.py:6-153, raft.py:112-123
+ * No torch types appear here.  The Python host side (ptlflow_b200/_lib.py) binds these
+ * symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative pfb_status otherwise; the message is
+ *     available from pfb_last_error() (thread local).  The Python shim raises RuntimeError,
+ *     mirroring TORCH_CHECK in correlation.cpp:19-21.
+ *   - nothing allocates: callers pass outputs and workspaces (sizes from pfb_*_bytes()).
+ *   - everything is asynchronous on `stream` (the reference plugin launches on the legacy
+ *     default stream, correlation_kernel.cu:278; here the caller's stream is explicit so
+ *     CUDA-graph capture and torch's current stream both work).
+ *   - activations are pixel-major ("NHWC"): [B, H, W, C] with C contiguous.  Coordinates and
+ *     flow are always fp32 [B, H, W, 2] with (x, y) interleaved.
+ *   - dtype is the STORAGE type of features / volume / activations / packed weights;
+ *     accumulation, coordinates, bilinear weights, gates and softmax are always fp32.
+ */
+#ifndef PTLFLOW_B200_H_
+#define PTLFLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PFB_API __attribute__((visibility("default")))
+#else
+#define PFB_API
+#endif
+
+typedef void* pfb_stream; /* cudaStream_t */
+
+typedef enum { PFB_F32 = 0, PFB_F16 = 1, PFB_BF16 = 2 } pfb_dtype;
+
+typedef enum {
+  PFB_OK = 0,
+  PFB_ERR_ARG = -1,     /* bad argument (null pointer, unsupported size / dtype) */
+  PFB_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed */
+  PFB_ERR_UNSUPPORTED = -3
+} pfb_status;
+
+#define PFB_MAX_LEVELS 8
+#define PFB_MAX_SRC 4
+
+PFB_API int pfb_version(void);
+PFB_API const char* pfb_last_error(void);
+/* sm major*10+minor of the current device, or negative status. */
+PFB_API int pfb_device_arch(void);
+
+/* ------------------------------------------------------------------------------------
+ * a1 + a2: all-pairs correlation volume and its pooled pyramid
+ *   replaces CorrBlock.corr + CorrBlock.__init__     ptlflow/models/raft/corr.py:13-27, 56-64
+ * fmap1, fmap2 : [B, H, W, C] dtype.   pyramid[l] : [B*H*W, H>>l, W>>l] dtype (floor sizes),
+ * level 0 = <f1, f2> / sqrt(C); level l = 2x2 mean of level l-1.
+ * impl: 0 = auto (tcgen05 tensor-core GEMM for f16/bf16 when the shape allows, else SIMT),
+ *       1 = force the SIMT fp32-accumulate kernel, 2 = force tcgen05.
+ * ---------------------------------------------------------------------------------- */
+PFB_API int pfb_corr_volume_build(const void* fmap1, const void* fmap2, void* const* pyramid, int B, int H, int W,
+                          int C, int levels, pfb_dtype dtype, int impl, pfb_stream stream);
+/* bytes of level l for the given feature-grid size (helper for callers that allocate). */
+PFB_API size_t pfb_corr_level_bytes(int B, int H, int W, int level, pfb_dtype dtype);
+
+/* ------------------------------------------------------------------------------------
+ * a3: multi-scale radius-r lookup     replaces CorrBlock.__call__   corr.py:29-54
+ * coords : [B, H, W, 2] fp32 absolute target coordinates (x, y).
+ * out    : channel = l*(2r+1)^2 + i*(2r+1) + j, sample at (x/2^l + i - r, y/2^l + j - r)  (x-major).
+ *          out_nchw = 0 -> [B, H, W, out_stride] (out_stride >= L*(2r+1)^2, extra channels zero-filled)
+ *          out_nchw = 1 -> [B, L*(2r+1)^2, H, W]  (the corr-block protocol layout)
+ * out_dtype may differ from the pyramid dtype (e.g. fp32 output from an fp16 volume).
+ * ---------------------------------------------------------------------------------- */
+PFB_API int pfb_corr_lookup(void* const* pyramid, const float* coords, void* out, int B, int H, int W, int levels,
+                    int radius, pfb_dtype dtype, pfb_dtype out_dtype, int out_nchw, int out_stride,
+                    pfb_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * a4: on-the-fly correlation + lookup (no 4D volume)
+ *   replaces AlternateCorrBlock.__call__     corr.py:78-101  (all levels, scaled by 1/sqrt(C))
+ * fmap1 : [B, H, W, C];  fmap2_pyramid[l] : [B, H>>l, W>>l, C] (level 0 = fmap2, l>0 pooled by
+ * pfb_avg_pool2x2_nhwc);  output as in pfb_corr_lookup.
+ * ---------------------------------------------------------------------------------- */
+PFB_API int pfb_corr_lookup_onthefly(const void* fmap1, void* const* fmap2_pyramid, const float* coords, void* out,
+                             int B, int H, int W, int C, int levels, int radius, pfb_dtype dtype,
+                             pfb_dtype out_dtype, int out_nchw, int out_stride, pfb_stream stream);
+
+/* The reference plugin's own entry point, same tensor contract:
+ *   alt_cuda_corr.forward(fmap1, fmap2, coords, radius) -> [corr]     correlation.cpp:23-33
+ * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C], coords [B,1,H1,W1,2] fp32, out [B,1,(2r+1)^2,H1,W1];
+ * unscaled dot products.  Unlike the reference (fp32 only, correlation_kernel.cu:278) the
+ * features may be f16/bf16; out is `out_dtype`. */
+PFB_API int pfb_alt_corr_forward(const void* fmap1, const void* fmap2, const float* coords, void* out, int B, int H1,
+                         int W1, int H2, int W2, int C, int radius, pfb_dtype dtype, pfb_dtype out_dtype,
+                         pfb_stream stream);
+
+/* 2x2 mean pooling of a pixel-major tensor [N, H, W, C] -> [N, H/2, W/2, C] (floor). */
+PFB_API int pfb_avg_pool2x2_nhwc(const void* in, void* out, int N, int H, int W, int C, pfb_dtype dtype,
+                         pfb_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * Convolution building block (stride 1, "same" zero padding, odd kernel), pixel-major.
+ * The input is the channel-concatenation of up to PFB_MAX_SRC tensors, so torch.cat copies
+ * of the reference (update.py:60,63,107,111,148) never happen.
+ * ---------------------------------------------------------------------------------- */
+typedef enum {
+  PFB_EPI_LINEAR = 0,  /* out = scale * (acc + bias)                                        */
+  PFB_EPI_RELU = 1,    /* out = relu(acc + bias)                                            */
+  PFB_EPI_GRU_ZR = 2,  /* cols [0,hd): z = sigmoid -> aux_z;  cols [hd,2hd): r = sigmoid,
+                          out = r * h                               update.py:61-63,68-70 */
+  PFB_EPI_GRU_Q = 3,   /* q = tanh(acc+bias); out = (1 - z) * h + z * q     update.py:63-64 */
+  PFB_EPI_FLOW = 4,    /* Cout = 2: coords1 += acc + bias (fp32, in place);
+                          out(fp32) = coords1 - grid               raft.py:174-178          */
+  PFB_EPI_RELU_APPEND_FLOW = 5 /* relu into cols [0,Cout) and copy flow(fp32 [.,2]) into the
+                          next two columns                          update.py:111-112      */
+} pfb_epilogue;
+
+typedef struct {
+  const void* ptr; /* [B, H, W, stride] */
+  int channels;    /* channels taken from this source */
+  int stride;      /* elements per pixel in memory (>= offset + channels) */
+  int offset;      /* first channel */
+  int is_f32;      /* 1: fp32 source regardless of `dtype` (flow / coordinates) */
+} pfb_conv_src;
+
+typedef struct {
+  pfb_conv_src src[PFB_MAX_SRC];
+  int nsrc;
+  int B, H, W;
+  int KH, KW;          /* odd; padding KH/2, KW/2 */
+  int Cout;            /* real output channels */
+  int Cout_pad;        /* row length of the packed weight (>= Cout) */
+  const void* weight;  /* packed by pfb_pack_conv_weight: [KH*KW][Cin_total][Cout_pad] dtype */
+  const float* bias;   /* [Cout] fp32 (may be NULL) */
+  int epilogue;        /* pfb_epilogue */
+  float scale;         /* PFB_EPI_LINEAR only */
+  void* out;           /* [B,H,W,out_stride] dtype (fp32 for PFB_EPI_FLOW) */
+  int out_stride, out_offset;
+  const void* aux_h;   /* GRU: hidden state [B,H,W,hd] dtype */
+  void* aux_z;         /* GRU: z gate buffer [B,H,W,hd] dtype (written by ZR, read by Q) */
+  int hidden;          /* hd */
+  float* coords;       /* PFB_EPI_FLOW: coords1 [B,H,W,2] fp32 in/out */
+  const float* flow;   /* PFB_EPI_RELU_APPEND_FLOW: [B,H,W,2] fp32 */
+  pfb_dtype dtype;
+  int impl;            /* 0 auto, 1 SIMT, 2 tcgen05 */
+} pfb_conv_params;
+
+PFB_API int pfb_conv2d(const pfb_conv_params* p, pfb_stream stream);
+
+/* torch-layout weight [Cout][Cin][KH][KW] (src_dtype) -> packed [KH*KW][Cin][Cout_pad] (dst_dtype),
+ * written at column `col_offset` (so convz|convr share one packed matrix).  Columns outside
+ * [col_offset, col_offset+Cout) are left untouched: zero the buffer first. */
+PFB_API int pfb_pack_conv_weight(const void* src, void* dst, int Cout, int Cin, int KH, int KW, int Cout_pad,
+                         int col_offset, pfb_dtype src_dtype, pfb_dtype dst_dtype, pfb_stream stream);
+/* dst[offset + i] = (float) src[i] */
+PFB_API int pfb_pack_bias(const void* src, float* dst, int n, int offset, pfb_dtype src_dtype, pfb_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * a10: upsampling
+ *   convex 8x : RAFT.upsample_flow               ptlflow/models/raft/raft.py:112-123
+ *   bilinear  : upflow8 (raft_small)             ptlflow/models/raft/utils.py:94-96
+ * coords : [B,H,W,2] fp32 (flow = coords - grid);  mask : [B,H,W,576] dtype, channel =
+ * tap*64 + sy*8 + sx, already scaled by 0.25.  out : [B, 2, out_h, out_w] fp32 (NCHW), the
+ * window of the 8H x 8W result starting at (pad_top, pad_left) -- i.e. already un-padded.
+ * flow_small (optional) : [B, 2, H, W] fp32.
+ * ---------------------------------------------------------------------------------- */
+PFB_API int pfb_convex_upsample(const float* coords, const void* mask, float* out, float* flow_small, int B, int H,
+                        int W, int out_h, int out_w, int pad_top, int pad_left, pfb_dtype dtype,
+                        pfb_stream stream);
+PFB_API int pfb_upflow8(const float* coords, float* out, float* flow_small, int B, int H, int W, int out_h, int out_w,
+                int pad_top, int pad_left, pfb_stream stream);
+
+/* cnet output [B,H,W,hd+cd] -> net = tanh(first hd), inp = relu(rest)     raft.py:155-158 */
+PFB_API int pfb_context_split(const void* cnet, void* net, void* inp, int B, int H, int W, int hidden, int context,
+                      pfb_dtype dtype, pfb_stream stream);
+/* coords[b,y,x] = (x, y) + (flow_init ? flow_init[b,:,y,x] (NCHW fp32) : 0)   raft.py:103-110,162-167 */
+PFB_API int pfb_init_coords(float* coords, const float* flow_init_nchw, int B, int H, int W, pfb_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * a6-a9, a11: the refinement loop   (BasicUpdateBlock / SmallUpdateBlock + RAFT.forward loop)
+ *   ptlflow/models/raft/update.py:115-153, ptlflow/models/raft/raft.py:170-192
+ * ---------------------------------------------------------------------------------- */
+typedef enum {
+  PFB_L_CONVC1 = 0, PFB_L_CONVC2, PFB_L_CONVF1, PFB_L_CONVF2, PFB_L_CONV,
+  PFB_L_GRU_ZR1, PFB_L_GRU_Q1, PFB_L_GRU_ZR2, PFB_L_GRU_Q2,
+  PFB_L_FLOW1, PFB_L_FLOW2, PFB_L_MASK1, PFB_L_MASK2,
+  PFB_L_COUNT
+} pfb_layer_id;
+
+typedef struct {
+  const void* weight; /* packed, see pfb_pack_conv_weight */
+  const float* bias;
+  int Cout, Cout_pad, Cin, KH, KW;
+} pfb_layer;
+
+typedef struct {
+  int variant;        /* 0 = raft (BasicUpdateBlock, SepConvGRU, convex upsample)
+                         1 = raft_small (SmallUpdateBlock, ConvGRU, bilinear upflow8) */
+  pfb_dtype dtype;
+  int B, H, W;        /* 1/8-resolution grid */
+  int feat_dim;       /* C of fmap1/fmap2 (on-the-fly mode) */
+  int corr_levels, corr_radius;
+  int hidden_dim, context_dim;
+  int iters;
+  int alternate_corr; /* 0: look up the materialised pyramid; 1: on-the-fly (a4) */
+  int out_h, out_w, pad_top, pad_left; /* full-resolution output window */
+  int impl;           /* 0 auto, 1 SIMT everywhere, 2 tcgen05 where available */
+} pfb_raft_cfg;
+
+typedef struct {
+  pfb_layer layers[PFB_L_COUNT];
+} pfb_raft_weights;
+
+typedef struct {
+  void* const* pyramid;       /* [corr_levels] volume levels, or (alternate_corr) fmap2 levels */
+  const void* fmap1;          /* alternate_corr only */
+  void* net;                  /* [B,H,W,hidden] dtype, in/out */
+  const void* inp;            /* [B,H,W,context] dtype */
+  float* coords;              /* [B,H,W,2] fp32, in/out (absolute target coordinates) */
+  float* flow_up;             /* [B,2,out_h,out_w] fp32 */
+  float* flow_small;          /* [B,2,H,W] fp32 */
+  void* workspace;            /* pfb_raft_workspace_bytes(cfg) */
+  size_t workspace_bytes;
+} pfb_raft_buffers;
+
+PFB_API size_t pfb_raft_workspace_bytes(const pfb_raft_cfg* cfg);
+/* Runs cfg->iters refinement iterations followed by the final upsample.  Only the last
+ * iteration evaluates the mask head (raft.py:192 returns only the last prediction in eval). */
+PFB_API int pfb_raft_refine(const pfb_raft_cfg* cfg, const pfb_raft_weights* w, const pfb_raft_buffers* buf,
+                    pfb_stream stream);
+/* One update iteration without the upsample (used by the operator-level parity tests);
+ * mask_out may be NULL. Lookup output ("corr") is taken from `corr` if non-NULL, otherwise
+ * computed from buf->pyramid. */
+PFB_API int pfb_raft_update_iter(const pfb_raft_cfg* cfg, const pfb_raft_weights* w, const pfb_raft_buffers* buf,
+                         const void* corr, void* mask_out, pfb_stream stream);
+
+/* ------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): launch accounting and live per-kernel-class timing.
+ * kernel_class: 0 volume, 1 pool, 2 lookup, 3 on-the-fly lookup, 4 conv, 5 upsample, 6 misc;
+ * -1 = all.  pfb_profile_collect synchronises the device, writes summed milliseconds and span
+ * counts per class (arrays of >= PFB_KERNEL_CLASSES entries) and clears the recorded spans.
+ * ---------------------------------------------------------------------------------- */
+#define PFB_KERNEL_CLASSES 7
+PFB_API unsigned long long pfb_launch_count(int kernel_class);
+PFB_API int pfb_profile_enable(int on);
+PFB_API int pfb_profile_collect(double* ms, unsigned long long* n, int len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTLFLOW_B200_H_ */

@@ -1,0 +1,159 @@
+"""ctypes binding of libptlflow_b200.so (the C ABI declared in include/ptlflow_b200.h).
+
+The library is the product: if it is missing this module raises -- there is no CPU or
+PyTorch fallback for the hot path.  Build it with ``python -m ptlflow_b200.csrc.build``
+(or ``__graft_entry__.build()``); the .so is kept in-tree under ptlflow_b200/lib/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libptlflow_b200.so")
+
+PFB_MAX_LEVELS = 8
+PFB_MAX_SRC = 4
+
+F32, F16, BF16 = 0, 1, 2
+_DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+EPI_LINEAR, EPI_RELU, EPI_GRU_ZR, EPI_GRU_Q, EPI_FLOW, EPI_RELU_APPEND_FLOW = range(6)
+
+(L_CONVC1, L_CONVC2, L_CONVF1, L_CONVF2, L_CONV, L_GRU_ZR1, L_GRU_Q1, L_GRU_ZR2, L_GRU_Q2,
+ L_FLOW1, L_FLOW2, L_MASK1, L_MASK2, L_COUNT) = range(14)
+
+
+class ConvSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("channels", C.c_int), ("stride", C.c_int), ("offset", C.c_int), ("is_f32", C.c_int)]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("src", ConvSrc * PFB_MAX_SRC), ("nsrc", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("KH", C.c_int), ("KW", C.c_int),
+        ("Cout", C.c_int), ("Cout_pad", C.c_int),
+        ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("epilogue", C.c_int), ("scale", C.c_float),
+        ("out", C.c_void_p), ("out_stride", C.c_int), ("out_offset", C.c_int),
+        ("aux_h", C.c_void_p), ("aux_z", C.c_void_p), ("hidden", C.c_int),
+        ("coords", C.c_void_p), ("flow", C.c_void_p),
+        ("dtype", C.c_int), ("impl", C.c_int),
+    ]
+
+
+class Layer(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("Cout", C.c_int), ("Cout_pad", C.c_int),
+                ("Cin", C.c_int), ("KH", C.c_int), ("KW", C.c_int)]
+
+
+class RaftCfg(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int), ("dtype", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("feat_dim", C.c_int), ("corr_levels", C.c_int), ("corr_radius", C.c_int),
+        ("hidden_dim", C.c_int), ("context_dim", C.c_int), ("iters", C.c_int), ("alternate_corr", C.c_int),
+        ("out_h", C.c_int), ("out_w", C.c_int), ("pad_top", C.c_int), ("pad_left", C.c_int), ("impl", C.c_int),
+    ]
+
+
+class RaftWeights(C.Structure):
+    _fields_ = [("layers", Layer * L_COUNT)]
+
+
+class RaftBuffers(C.Structure):
+    _fields_ = [
+        ("pyramid", C.POINTER(C.c_void_p)), ("fmap1", C.c_void_p), ("net", C.c_void_p), ("inp", C.c_void_p),
+        ("coords", C.c_void_p), ("flow_up", C.c_void_p), ("flow_small", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+# name -> (restype, argtypes); every symbol include/ptlflow_b200.h declares
+_I, _P, _S = C.c_int, C.c_void_p, C.c_void_p
+_PP = C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "pfb_version": (_I, []),
+    "pfb_last_error": (C.c_char_p, []),
+    "pfb_device_arch": (_I, []),
+    "pfb_corr_volume_build": (_I, [_P, _P, _PP, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_corr_level_bytes": (C.c_size_t, [_I, _I, _I, _I, _I]),
+    "pfb_corr_lookup": (_I, [_PP, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_corr_lookup_onthefly": (_I, [_P, _PP, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_alt_corr_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_avg_pool2x2_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
+    "pfb_conv2d": (_I, [C.POINTER(ConvParams), _S]),
+    "pfb_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_pack_bias": (_I, [_P, _P, _I, _I, _I, _S]),
+    "pfb_convex_upsample": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_upflow8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_context_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_init_coords": (_I, [_P, _P, _I, _I, _I, _S]),
+    "pfb_raft_workspace_bytes": (C.c_size_t, [C.POINTER(RaftCfg)]),
+    "pfb_raft_refine": (_I, [C.POINTER(RaftCfg), C.POINTER(RaftWeights), C.POINTER(RaftBuffers), _S]),
+    "pfb_launch_count": (C.c_ulonglong, [_I]),
+    "pfb_profile_enable": (_I, [_I]),
+    "pfb_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), _I]),
+    "pfb_raft_update_iter": (_I, [C.POINTER(RaftCfg), C.POINTER(RaftWeights), C.POINTER(RaftBuffers), _P, _P, _S]),
+}
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the shared library.  Raises LibraryMissing if it was never built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not found: the ptlflow_b200 hot path is hand-written CUDA and has no fallback. "
+            "Build it with `python -m ptlflow_b200.csrc.build` (needs nvcc, no GPU required to compile)."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    """Translate a negative pfb_status into RuntimeError (the reference plugin raises RuntimeError
+    through TORCH_CHECK, ptlflow/utils/external/alt_cuda_corr/correlation.cpp:19-21)."""
+    if rc != 0:
+        msg = load().pfb_last_error().decode(errors="replace")
+        raise RuntimeError(f"ptlflow_b200 {what} failed (status {rc}): {msg}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise RuntimeError(f"ptlflow_b200: unsupported dtype {dt}; use float32, float16 or bfloat16") from None
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    """Mirror of CHECK_INPUT (correlation.cpp:19-21): CUDA + contiguous, else RuntimeError."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def ptr_array(tensors) -> "C.Array":
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr

@@ -1,0 +1,220 @@
+// Host-side orchestration of the refinement loop: lookup -> motion encoder -> GRU -> heads,
+// `iters` times, then the upsample.  Mirrors the data flow of
+//   ptlflow/models/raft/raft.py:170-192 and ptlflow/models/raft/update.py:115-153
+// but every stage is one launch of this library's kernels on the caller's stream (so the whole
+// loop can be captured in a CUDA graph by the host), no torch.cat / permute copies exist, and
+// the mask head + upsample run once (eval returns only the last prediction, raft.py:192).
+#include <initializer_list>
+
+#include "common.cuh"
+
+namespace pfb {
+
+int launch_flow_from_coords(const float* coords, float* flow, int B, int H, int W, cudaStream_t s);
+
+struct Workspace {
+  // element strides (channels per pixel) and byte offsets inside the caller's workspace
+  int planes, corr_stride;
+  size_t off_corr, off_cor1, off_corflo, off_flo1, off_motion, off_z, off_rh, off_fh, off_mh, off_mask, off_flow;
+  size_t total;
+  int c_cor1, c_corflo, c_cor2, c_flo1, c_flo2, c_motion, c_fh;
+};
+
+static Workspace plan(const pfb_raft_cfg* c) {
+  Workspace w{};
+  const size_t P = (size_t)c->B * c->H * c->W;
+  const size_t es = dtype_size(c->dtype);
+  const int K = 2 * c->corr_radius + 1;
+  w.planes = c->corr_levels * K * K;
+  // tensor-core path wants 64-channel (128-byte) K chunks; pad columns are zero-filled by the lookup
+  w.corr_stride = (c->dtype == PFB_F32) ? w.planes : (int)align_up(w.planes, 64);
+  if (c->variant == 0) {
+    w.c_cor1 = 256; w.c_cor2 = 192; w.c_flo1 = 128; w.c_flo2 = 64; w.c_motion = 128; w.c_fh = 256;
+  } else {
+    w.c_cor1 = 0; w.c_cor2 = 96; w.c_flo1 = 64; w.c_flo2 = 32; w.c_motion = 82; w.c_fh = 128;
+  }
+  w.c_corflo = w.c_cor2 + w.c_flo2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  w.off_corr = take(P * w.corr_stride * es);
+  w.off_cor1 = take(P * (size_t)w.c_cor1 * es);
+  w.off_corflo = take(P * (size_t)w.c_corflo * es);
+  w.off_flo1 = take(P * (size_t)w.c_flo1 * es);
+  w.off_motion = take(P * (size_t)w.c_motion * es);
+  w.off_z = take(P * (size_t)c->hidden_dim * es);
+  w.off_rh = take(P * (size_t)c->hidden_dim * es);
+  w.off_fh = take(P * (size_t)w.c_fh * es);
+  w.off_mh = take(c->variant == 0 ? P * 256 * es : 0);
+  w.off_mask = take(c->variant == 0 ? P * 576 * es : 0);
+  w.off_flow = take(P * 2 * sizeof(float));
+  w.total = off;
+  return w;
+}
+
+static int check_cfg(const pfb_raft_cfg* c) {
+  PFB_CHECK_ARG(c, "raft: null cfg");
+  PFB_CHECK_ARG(c->variant == 0 || c->variant == 1, "raft: variant=%d", c->variant);
+  PFB_CHECK_ARG(dtype_ok(c->dtype), "raft: bad dtype");
+  PFB_CHECK_ARG(c->B > 0 && c->H > 0 && c->W > 0, "raft: bad grid %dx%dx%d", c->B, c->H, c->W);
+  PFB_CHECK_ARG(c->corr_levels >= 1 && c->corr_levels <= PFB_MAX_LEVELS && c->corr_radius >= 0 && c->corr_radius <= 15,
+                "raft: corr_levels=%d corr_radius=%d", c->corr_levels, c->corr_radius);
+  PFB_CHECK_ARG((c->H >> (c->corr_levels - 1)) >= 1 && (c->W >> (c->corr_levels - 1)) >= 1,
+                "raft: %dx%d grid too small for %d levels", c->H, c->W, c->corr_levels);
+  PFB_CHECK_ARG(c->hidden_dim > 0 && c->context_dim > 0 && c->iters >= 0, "raft: bad dims");
+  if (c->variant == 0) PFB_CHECK_ARG(c->hidden_dim == 128 && c->context_dim == 128, "raft: BasicUpdateBlock expects hidden=context=128");
+  else PFB_CHECK_ARG(c->hidden_dim == 96 && c->context_dim == 64, "raft_small: SmallUpdateBlock expects hidden=96 context=64");
+  return PFB_OK;
+}
+
+struct Ctx {
+  const pfb_raft_cfg* c;
+  const pfb_raft_weights* w;
+  const pfb_raft_buffers* b;
+  Workspace ws;
+  char* base;
+  cudaStream_t s;
+  void* at(size_t off) const { return base + off; }
+};
+
+static pfb_conv_src src_of(const void* ptr, int channels, int stride, int offset = 0, int is_f32 = 0) {
+  pfb_conv_src s;
+  s.ptr = ptr; s.channels = channels; s.stride = stride; s.offset = offset; s.is_f32 = is_f32;
+  return s;
+}
+
+static int run_conv(const Ctx& x, int layer, std::initializer_list<pfb_conv_src> srcs, int epi, void* out,
+                    int out_stride, int out_offset, float scale = 1.f) {
+  const pfb_layer& L = x.w->layers[layer];
+  PFB_CHECK_ARG(L.weight, "raft: layer %d has no packed weight", layer);
+  pfb_conv_params p{};
+  int i = 0, cin = 0;
+  for (const auto& s : srcs) { p.src[i++] = s; cin += s.channels; }
+  p.nsrc = i;
+  // the lookup buffer may be wider than the layer's real Cin (zero pad columns <-> zero weight rows)
+  PFB_CHECK_ARG(cin == L.Cin, "raft: layer %d expects Cin=%d, sources provide %d", layer, L.Cin, cin);
+  p.B = x.c->B; p.H = x.c->H; p.W = x.c->W;
+  p.KH = L.KH; p.KW = L.KW; p.Cout = L.Cout; p.Cout_pad = L.Cout_pad;
+  p.weight = L.weight; p.bias = L.bias;
+  p.epilogue = epi; p.scale = scale;
+  p.out = out; p.out_stride = out_stride; p.out_offset = out_offset;
+  p.aux_h = x.b->net; p.aux_z = x.at(x.ws.off_z); p.hidden = x.c->hidden_dim;
+  p.coords = x.b->coords; p.flow = reinterpret_cast<const float*>(x.at(x.ws.off_flow));
+  p.dtype = x.c->dtype; p.impl = x.c->impl;
+  return pfb_conv2d(&p, (pfb_stream)x.s);
+}
+
+#define PFB_TRY(expr)        \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != PFB_OK) return rc__; \
+  } while (0)
+
+static int lookup(const Ctx& x) {
+  const pfb_raft_cfg* c = x.c;
+  if (c->alternate_corr)
+    return pfb_corr_lookup_onthefly(x.b->fmap1, x.b->pyramid, x.b->coords, x.at(x.ws.off_corr), c->B, c->H, c->W,
+                                    c->feat_dim, c->corr_levels, c->corr_radius, c->dtype, c->dtype, 0,
+                                    x.ws.corr_stride, (pfb_stream)x.s);
+  return pfb_corr_lookup(x.b->pyramid, x.b->coords, x.at(x.ws.off_corr), c->B, c->H, c->W, c->corr_levels,
+                         c->corr_radius, c->dtype, c->dtype, 0, x.ws.corr_stride, (pfb_stream)x.s);
+}
+
+// One BasicUpdateBlock / SmallUpdateBlock evaluation + coords update.  update.py:122-153
+static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
+  const pfb_raft_cfg* c = x.c;
+  const Workspace& ws = x.ws;
+  const int hd = c->hidden_dim, cd = c->context_dim;
+  const void* corr = corr_ext ? corr_ext : x.at(ws.off_corr);
+  const int corr_stride = corr_ext ? ws.planes : ws.corr_stride;
+  void* corflo = x.at(ws.off_corflo);
+  void* flo1 = x.at(ws.off_flo1);
+  void* motion = x.at(ws.off_motion);
+  void* rh = x.at(ws.off_rh);
+  void* fh = x.at(ws.off_fh);
+  float* flow = reinterpret_cast<float*>(x.at(ws.off_flow));
+
+  // ---- motion encoder (update.py:76-112) ----
+  if (c->variant == 0) {
+    void* cor1 = x.at(ws.off_cor1);
+    PFB_TRY(run_conv(x, PFB_L_CONVC1, {src_of(corr, ws.planes, corr_stride)}, PFB_EPI_RELU, cor1, ws.c_cor1, 0));
+    PFB_TRY(run_conv(x, PFB_L_CONVC2, {src_of(cor1, ws.c_cor1, ws.c_cor1)}, PFB_EPI_RELU, corflo, ws.c_corflo, 0));
+  } else {
+    PFB_TRY(run_conv(x, PFB_L_CONVC1, {src_of(corr, ws.planes, corr_stride)}, PFB_EPI_RELU, corflo, ws.c_corflo, 0));
+  }
+  PFB_TRY(run_conv(x, PFB_L_CONVF1, {src_of(flow, 2, 2, 0, 1)}, PFB_EPI_RELU, flo1, ws.c_flo1, 0));
+  PFB_TRY(run_conv(x, PFB_L_CONVF2, {src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU, corflo, ws.c_corflo, ws.c_cor2));
+  PFB_TRY(run_conv(x, PFB_L_CONV, {src_of(corflo, ws.c_corflo, ws.c_corflo)}, PFB_EPI_RELU_APPEND_FLOW, motion, ws.c_motion, 0));
+
+  // ---- GRU (update.py:24-32 ConvGRU, :58-73 SepConvGRU); x = [inp, motion] ----
+  const int halves = (c->variant == 0) ? 2 : 1;
+  for (int h = 0; h < halves; ++h) {
+    const int lzr = h == 0 ? PFB_L_GRU_ZR1 : PFB_L_GRU_ZR2, lq = h == 0 ? PFB_L_GRU_Q1 : PFB_L_GRU_Q2;
+    PFB_TRY(run_conv(x, lzr, {src_of(x.b->net, hd, hd), src_of(x.b->inp, cd, cd), src_of(motion, ws.c_motion, ws.c_motion)},
+                     PFB_EPI_GRU_ZR, rh, hd, 0));
+    PFB_TRY(run_conv(x, lq, {src_of(rh, hd, hd), src_of(x.b->inp, cd, cd), src_of(motion, ws.c_motion, ws.c_motion)},
+                     PFB_EPI_GRU_Q, x.b->net, hd, 0));
+  }
+
+  // ---- heads (update.py:6-14, :138-152) ----
+  PFB_TRY(run_conv(x, PFB_L_FLOW1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, fh, ws.c_fh, 0));
+  PFB_TRY(run_conv(x, PFB_L_FLOW2, {src_of(fh, ws.c_fh, ws.c_fh)}, PFB_EPI_FLOW, flow, 2, 0));
+  if (mask_out && c->variant == 0) {
+    void* mh = x.at(ws.off_mh);
+    PFB_TRY(run_conv(x, PFB_L_MASK1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, mh, 256, 0));
+    PFB_TRY(run_conv(x, PFB_L_MASK2, {src_of(mh, 256, 256)}, PFB_EPI_LINEAR, mask_out, 576, 0, 0.25f));
+  }
+  return PFB_OK;
+}
+
+static int make_ctx(Ctx& x, const pfb_raft_cfg* cfg, const pfb_raft_weights* w, const pfb_raft_buffers* buf,
+                    cudaStream_t s, bool need_pyramid) {
+  PFB_TRY(check_cfg(cfg));
+  PFB_CHECK_ARG(w && buf, "raft: null weights/buffers");
+  PFB_CHECK_ARG(buf->net && buf->inp && buf->coords && buf->workspace, "raft: null state buffer");
+  if (need_pyramid) {
+    PFB_CHECK_ARG(buf->pyramid, "raft: null pyramid");
+    PFB_CHECK_ARG(!cfg->alternate_corr || (buf->fmap1 && cfg->feat_dim > 0), "raft: alternate_corr needs fmap1 and feat_dim");
+  }
+  x.c = cfg; x.w = w; x.b = buf; x.s = s;
+  x.ws = plan(cfg);
+  PFB_CHECK_ARG(buf->workspace_bytes >= x.ws.total, "raft: workspace %zu bytes < required %zu", buf->workspace_bytes, x.ws.total);
+  x.base = reinterpret_cast<char*>(buf->workspace);
+  return PFB_OK;
+}
+
+}  // namespace pfb
+
+using namespace pfb;
+
+extern "C" PFB_API size_t pfb_raft_workspace_bytes(const pfb_raft_cfg* cfg) {
+  if (check_cfg(cfg) != PFB_OK) return 0;
+  return plan(cfg).total;
+}
+
+extern "C" PFB_API int pfb_raft_update_iter(const pfb_raft_cfg* cfg, const pfb_raft_weights* w, const pfb_raft_buffers* buf,
+                                    const void* corr, void* mask_out, pfb_stream stream) {
+  Ctx x;
+  PFB_TRY(make_ctx(x, cfg, w, buf, as_stream(stream), corr == nullptr));
+  PFB_TRY(launch_flow_from_coords(buf->coords, reinterpret_cast<float*>(x.at(x.ws.off_flow)), cfg->B, cfg->H, cfg->W, x.s));
+  if (!corr) PFB_TRY(lookup(x));
+  return update_iter(x, corr, mask_out);
+}
+
+extern "C" PFB_API int pfb_raft_refine(const pfb_raft_cfg* cfg, const pfb_raft_weights* w, const pfb_raft_buffers* buf,
+                               pfb_stream stream) {
+  Ctx x;
+  PFB_TRY(make_ctx(x, cfg, w, buf, as_stream(stream), true));
+  PFB_CHECK_ARG(buf->flow_up, "raft_refine: null flow_up");
+  PFB_CHECK_ARG(cfg->variant == 1 || cfg->iters >= 1, "raft_refine: the convex upsample needs at least one iteration (mask)");
+  PFB_TRY(launch_flow_from_coords(buf->coords, reinterpret_cast<float*>(x.at(x.ws.off_flow)), cfg->B, cfg->H, cfg->W, x.s));
+  void* mask = cfg->variant == 0 ? x.at(x.ws.off_mask) : nullptr;
+  for (int it = 0; it < cfg->iters; ++it) {
+    PFB_TRY(lookup(x));
+    PFB_TRY(update_iter(x, nullptr, it == cfg->iters - 1 ? mask : nullptr));
+  }
+  if (cfg->variant == 0)
+    return pfb_convex_upsample(buf->coords, mask, buf->flow_up, buf->flow_small, cfg->B, cfg->H, cfg->W, cfg->out_h,
+                               cfg->out_w, cfg->pad_top, cfg->pad_left, cfg->dtype, stream);
+  return pfb_upflow8(buf->coords, buf->flow_up, buf->flow_small, cfg->B, cfg->H, cfg->W, cfg->out_h, cfg->out_w,
+                     cfg->pad_top, cfg->pad_left, stream);
+}

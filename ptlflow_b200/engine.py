@@ -1,0 +1,109 @@
+"""RaftEngine: packed weights + workspaces + one C call for the whole refinement loop.
+
+This is the host-side glue between the kept ``RAFT.forward`` structure
+(ptlflow/models/raft/raft.py:125-194) and ``pfb_raft_refine``.  It owns nothing numerical:
+packing, buffers, pointer structs, CUDA-graph capture.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import check, dtype_code, load, ptr_array, stream_ptr
+
+
+class RaftEngine:
+    """Built lazily at first forward and rebuilt when the parameters' dtype / device / storage
+    change (callers do ``model.eval().cuda().half()`` *after* construction and after
+    ``load_state_dict`` -- model_benchmark.py:274-279, infer.py:148-152)."""
+
+    def __init__(self, update_block: torch.nn.Module, variant: int, hidden_dim: int, context_dim: int,
+                 corr_levels: int, corr_radius: int, dtype: torch.dtype, device: torch.device, impl: int = 0):
+        self.variant, self.hidden_dim, self.context_dim = variant, hidden_dim, context_dim
+        self.corr_levels, self.corr_radius = corr_levels, corr_radius
+        self.dtype, self.device, self.impl = dtype, device, impl
+        ub = update_block
+        enc, gru, fh = ub.encoder, ub.gru, ub.flow_head
+        P = lambda *convs: ops.PackedConv(convs, dtype, device)  # noqa: E731
+        layers: Dict[int, ops.PackedConv] = {}
+        layers[_lib.L_CONVC1] = P(enc.convc1)
+        layers[_lib.L_CONVF1] = P(enc.convf1)
+        layers[_lib.L_CONVF2] = P(enc.convf2)
+        layers[_lib.L_CONV] = P(enc.conv)
+        layers[_lib.L_FLOW1] = P(fh.conv1)
+        layers[_lib.L_FLOW2] = P(fh.conv2)
+        if variant == 0:
+            layers[_lib.L_CONVC2] = P(enc.convc2)
+            layers[_lib.L_GRU_ZR1] = P(gru.convz1, gru.convr1)  # z | r share the input: one GEMM, N = 2*hidden
+            layers[_lib.L_GRU_Q1] = P(gru.convq1)
+            layers[_lib.L_GRU_ZR2] = P(gru.convz2, gru.convr2)
+            layers[_lib.L_GRU_Q2] = P(gru.convq2)
+            layers[_lib.L_MASK1] = P(ub.mask[0])
+            layers[_lib.L_MASK2] = P(ub.mask[2])
+        else:
+            layers[_lib.L_GRU_ZR1] = P(gru.convz, gru.convr)
+            layers[_lib.L_GRU_Q1] = P(gru.convq)
+        self.layers = layers
+        self.weights = _lib.RaftWeights()
+        for k, v in layers.items():
+            self.weights.layers[k] = v.layer_struct()
+        self._workspaces: Dict[Tuple, torch.Tensor] = {}
+        self.signature = self.param_signature(update_block)
+
+    # -- cache invalidation --------------------------------------------------------------------
+    @staticmethod
+    def param_signature(update_block: torch.nn.Module):
+        return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in update_block.parameters())
+
+    # -- run --------------------------------------------------------------------------------
+    def make_cfg(self, B: int, H: int, W: int, iters: int, out_hw, pad, alternate_corr: bool, feat_dim: int) -> _lib.RaftCfg:
+        return _lib.RaftCfg(self.variant, dtype_code(self.dtype), B, H, W, feat_dim, self.corr_levels, self.corr_radius,
+                            self.hidden_dim, self.context_dim, iters, int(alternate_corr), out_hw[0], out_hw[1], pad[0], pad[1],
+                            self.impl)
+
+    def workspace(self, cfg: _lib.RaftCfg) -> torch.Tensor:
+        key = (cfg.B, cfg.H, cfg.W)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            nbytes = load().pfb_raft_workspace_bytes(C.byref(cfg))
+            if nbytes == 0:
+                check(-1, "raft_workspace_bytes")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._workspaces = {key: ws}  # keep one shape resident (bounded memory)
+        return ws
+
+    def refine(self, pyramid: Sequence[torch.Tensor], net: torch.Tensor, inp: torch.Tensor, coords: torch.Tensor,
+               iters: int, out_hw, pad, fmap1: Optional[torch.Tensor] = None):
+        """Runs the loop in place on (net, coords); returns (flow_up fp32 [B,2,oh,ow], flow_small fp32 [B,2,H,W])."""
+        B, H, W, _ = net.shape
+        alt = fmap1 is not None
+        cfg = self.make_cfg(B, H, W, iters, out_hw, pad, alt, fmap1.shape[-1] if alt else 0)
+        ws = self.workspace(cfg)
+        flow_up = torch.empty((B, 2, out_hw[0], out_hw[1]), dtype=torch.float32, device=self.device)
+        flow_small = torch.empty((B, 2, H, W), dtype=torch.float32, device=self.device)
+        pyr = ptr_array(pyramid)
+        buf = _lib.RaftBuffers(C.cast(pyr, C.POINTER(C.c_void_p)), fmap1.data_ptr() if alt else None, net.data_ptr(),
+                               inp.data_ptr(), coords.data_ptr(), flow_up.data_ptr(), flow_small.data_ptr(),
+                               ws.data_ptr(), ws.numel())
+        with torch.cuda.device(self.device):
+            check(load().pfb_raft_refine(C.byref(cfg), C.byref(self.weights), C.byref(buf), stream_ptr(self.device)), "raft_refine")
+        return flow_up, flow_small
+
+    def update_iter(self, net: torch.Tensor, inp: torch.Tensor, coords: torch.Tensor, corr: Optional[torch.Tensor] = None,
+                    pyramid: Optional[Sequence[torch.Tensor]] = None, want_mask: bool = False):
+        """One update-block evaluation (operator-level tests).  corr: pixel-major [B,H,W,planes]."""
+        B, H, W, _ = net.shape
+        cfg = self.make_cfg(B, H, W, 1, (8 * H, 8 * W), (0, 0), False, 0)
+        ws = self.workspace(cfg)
+        mask = torch.empty((B, H, W, 576), dtype=self.dtype, device=self.device) if (want_mask and self.variant == 0) else None
+        pyr = ptr_array(pyramid) if pyramid is not None else None
+        buf = _lib.RaftBuffers(C.cast(pyr, C.POINTER(C.c_void_p)) if pyr is not None else None, None, net.data_ptr(), inp.data_ptr(),
+                               coords.data_ptr(), None, None, ws.data_ptr(), ws.numel())
+        with torch.cuda.device(self.device):
+            check(load().pfb_raft_update_iter(C.byref(cfg), C.byref(self.weights), C.byref(buf),
+                                              corr.data_ptr() if corr is not None else None,
+                                              mask.data_ptr() if mask is not None else None, stream_ptr(self.device)), "raft_update_iter")
+        return mask

@@ -1,0 +1,1 @@
+from .raft import *  # noqa: F401,F403  (registers raft, raft_small)

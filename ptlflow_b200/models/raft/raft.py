@@ -1,0 +1,164 @@
+"""RAFT / RAFTSmall behind the reference's model surface, running on libptlflow_b200.
+
+Kept from the reference (ptlflow/models/raft/raft.py:48-247): class names, constructor keywords
+(= hparams / CLI flags), ``state_dict`` keys, ``forward(inputs: dict) -> dict`` with ``flows``
+[B,1,2,H,W] and ``flow_small`` [B,2,H/8,W/8], the warm-start input ``prev_preds.flow_small``.
+Replaced: everything between the encoders and the returned flow -- correlation volume + pyramid,
+the ``iters`` x {lookup, motion encoder, (Sep)ConvGRU, flow head}, mask head and the convex
+upsample run as hand-written sm_100a kernels through one C call (ptlflow_b200/engine.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...engine import RaftEngine
+from ...utils.registry import ptlflow_trained, register_model, trainable
+from ..base_model.base_model import BaseModel
+from .extractor import BasicEncoder, SmallEncoder
+from .update import BasicUpdateBlock, SmallUpdateBlock
+
+
+class SequenceLoss(nn.Module):
+    """Exponentially weighted L1 over the prediction sequence (training only; kept because the
+    constructor stores it as ``loss_fn``)."""
+
+    def __init__(self, gamma: float, max_flow: float) -> None:
+        super().__init__()
+        self.gamma, self.max_flow = gamma, max_flow
+
+    def forward(self, outputs, inputs):
+        preds = outputs["flow_preds"]
+        gt, valid = inputs["flows"][:, 0], inputs["valids"][:, 0]
+        valid = (valid >= 0.5) & (gt.pow(2).sum(dim=1, keepdim=True).sqrt() < self.max_flow)
+        n = len(preds)
+        return sum(self.gamma ** (n - i - 1) * (valid * (p - gt).abs()).mean() for i, p in enumerate(preds))
+
+
+class RAFT(BaseModel):
+    pretrained_checkpoints = {
+        "chairs": "https://github.com/hmorimitsu/ptlflow/releases/download/weights1/raft-chairs-590f38f7.ckpt",
+        "things": "https://github.com/hmorimitsu/ptlflow/releases/download/weights1/raft-things-802bbcfd.ckpt",
+        "sintel": "https://github.com/hmorimitsu/ptlflow/releases/download/weights1/raft-sintel-fb44381e.ckpt",
+        "kitti": "https://github.com/hmorimitsu/ptlflow/releases/download/weights1/raft-kitti-3a831a4b.ckpt",
+    }
+    _variant = 0  # pfb_raft_cfg.variant
+
+    def __init__(self, corr_levels: int = 4, corr_radius: int = 4, dropout: float = 0.0, gamma: float = 0.8,
+                 max_flow: float = 400, iters: int = 32, alternate_corr: bool = False, **kwargs) -> None:
+        super().__init__(output_stride=8, loss_fn=SequenceLoss(gamma, max_flow), **kwargs)
+        self.corr_levels, self.corr_radius = corr_levels, corr_radius
+        self.dropout, self.gamma, self.max_flow = dropout, gamma, max_flow
+        self.iters, self.alternate_corr = iters, alternate_corr
+        self.has_trained_on_ptlflow = True
+        # backend knobs (not hparams): 0 auto, 1 SIMT fp32-accumulate kernels, 2 force tcgen05
+        self.kernel_impl = 0
+        self.strict_fp32 = True  # fp32 models: keep cuDNN off TF32 so the 1e-3 parity gate holds
+        self._engine: Optional[RaftEngine] = None
+        self._build_networks()
+
+    def _build_networks(self) -> None:
+        self.hidden_dim = self.context_dim = 128
+        self.fnet = BasicEncoder(output_dim=256, norm_fn="instance", dropout=self.dropout)
+        self.cnet = BasicEncoder(output_dim=self.hidden_dim + self.context_dim, norm_fn="batch", dropout=self.dropout)
+        self.update_block = BasicUpdateBlock(self.corr_levels, self.corr_radius, hidden_dim=self.hidden_dim)
+
+    def freeze_bn(self) -> None:
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    # -- engine lifecycle ------------------------------------------------------------------
+    def _get_engine(self, dtype: torch.dtype, device: torch.device) -> RaftEngine:
+        eng = self._engine
+        if (eng is None or eng.dtype != dtype or eng.device != device or eng.impl != self.kernel_impl
+                or eng.corr_levels != self.corr_levels or eng.corr_radius != self.corr_radius
+                or eng.signature != RaftEngine.param_signature(self.update_block)):
+            eng = RaftEngine(self.update_block, self._variant, self.hidden_dim, self.context_dim, self.corr_levels,
+                             self.corr_radius, dtype, device, impl=self.kernel_impl)
+            self._engine = eng
+        return eng
+
+    def _encode(self, image1: torch.Tensor, image2: torch.Tensor):
+        x1 = image1.contiguous(memory_format=torch.channels_last)
+        x2 = image2.contiguous(memory_format=torch.channels_last)
+        if x1.dtype == torch.float32 and self.strict_fp32:
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                fmap1, fmap2 = self.fnet([x1, x2])
+                cnet = self.cnet(x1)
+        else:
+            fmap1, fmap2 = self.fnet([x1, x2])
+            cnet = self.cnet(x1)
+        return ops.to_pixel_major(fmap1), ops.to_pixel_major(fmap2), ops.to_pixel_major(cnet)
+
+    def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Estimate optical flow between a pair of frames (eval semantics of raft.py:125-194)."""
+        images = inputs["images"]
+        if not images.is_cuda:
+            raise RuntimeError("ptlflow_b200 runs on CUDA (sm_100a) only: move the model and inputs to the GPU. There is no CPU path.")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.update_block.parameters()) and self.training:
+            raise NotImplementedError("ptlflow_b200 implements the inference hot path; call under torch.no_grad() / model.eval()")
+        with torch.no_grad():
+            images, resizer = self.preprocess_images(images, bgr_add=-0.5, bgr_mult=2.0, bgr_to_rgb=True, resize_mode="pad",
+                                                     pad_mode="replicate", pad_two_side=True)
+            B = images.shape[0]
+            fmap1, fmap2, cnet = self._encode(images[:, 0], images[:, 1])
+            _, H8, W8, _ = fmap1.shape
+            eng = self._get_engine(fmap1.dtype, fmap1.device)
+            net, inp = ops.context_split(cnet, self.hidden_dim, self.context_dim)
+
+            flow_init = None
+            prev = inputs.get("prev_preds")
+            if prev is not None and prev.get("flow_small") is not None:
+                from ...utils.warm_start import forward_interpolate_batch
+
+                flow_init = forward_interpolate_batch(prev["flow_small"])
+            coords = ops.init_coords(B, H8, W8, fmap1.device, flow_init)
+
+            if self.alternate_corr:
+                pyramid, f1 = ops.feature_pyramid(fmap2, self.corr_levels), fmap1
+            else:
+                pyramid, f1 = ops.corr_volume_build(fmap1, fmap2, self.corr_levels, impl=self.kernel_impl), None
+
+            orig_h, orig_w = inputs["images"].shape[-2:]
+            pad_top, pad_left = resizer.pad_top_left
+            flow_up, flow_small = eng.refine(pyramid, net, inp, coords, self.iters, (orig_h, orig_w), (pad_top, pad_left), fmap1=f1)
+            flow_up = self.postprocess_predictions(flow_up, resizer, is_flow=True)  # no-op: written un-padded
+            out_dtype = inputs["images"].dtype
+            return {"flows": flow_up.to(out_dtype)[:, None], "flow_small": flow_small.to(out_dtype),
+                    "flows_fp32": flow_up[:, None]}
+
+
+class RAFTSmall(RAFT):
+    pretrained_checkpoints = {
+        "things": "https://github.com/hmorimitsu/ptlflow/releases/download/weights1/raft_small-things-b7d9f997.ckpt"
+    }
+    _variant = 1
+
+    def __init__(self, corr_levels: int = 4, corr_radius: int = 3, dropout: float = 0.0, gamma: float = 0.8,
+                 max_flow: float = 400, iters: int = 32, alternate_corr: bool = False, **kwargs) -> None:
+        super().__init__(corr_levels=corr_levels, corr_radius=corr_radius, dropout=dropout, gamma=gamma, max_flow=max_flow,
+                         iters=iters, alternate_corr=alternate_corr, **kwargs)
+
+    def _build_networks(self) -> None:
+        self.hidden_dim, self.context_dim = 96, 64
+        self.fnet = SmallEncoder(output_dim=128, norm_fn="instance", dropout=self.dropout)
+        self.cnet = SmallEncoder(output_dim=self.hidden_dim + self.context_dim, norm_fn="none", dropout=self.dropout)
+        self.update_block = SmallUpdateBlock(self.corr_levels, self.corr_radius, hidden_dim=self.hidden_dim)
+
+
+@register_model
+@trainable
+@ptlflow_trained
+class raft(RAFT):
+    pass
+
+
+@register_model
+@trainable
+@ptlflow_trained
+class raft_small(RAFTSmall):
+    pass

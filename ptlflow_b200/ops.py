@@ -1,0 +1,226 @@
+"""Tensor-level wrappers over the C ABI (plumbing only: pointers, shapes, current stream).
+
+Layout conventions (see include/ptlflow_b200.h): feature / activation tensors are pixel-major
+``[B, H, W, C]``; coordinates are fp32 ``[B, H, W, 2]`` with (x, y) interleaved.  Helpers at the
+bottom convert from/to the reference's NCHW tensors without a copy when the tensor is already
+channels_last.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, load, ptr_array, require_cuda, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------
+# layout helpers
+# ------------------------------------------------------------------------------------------
+def to_pixel_major(x: torch.Tensor) -> torch.Tensor:
+    """NCHW (any memory format) -> contiguous [B,H,W,C]; free when x is channels_last."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def coords_to_pixel_major(coords: torch.Tensor) -> torch.Tensor:
+    """[B,2,H,W] any float dtype -> fp32 [B,H,W,2]."""
+    return coords.permute(0, 2, 3, 1).float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# a1 + a2
+# ------------------------------------------------------------------------------------------
+def alloc_pyramid(B: int, H: int, W: int, levels: int, dtype: torch.dtype, device) -> List[torch.Tensor]:
+    return [torch.empty((B * H * W, H >> l, W >> l), dtype=dtype, device=device) for l in range(levels)]
+
+
+def corr_volume_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int = 4, impl: int = 0,
+                      out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """fmap [B,H,W,C] -> [level0 [B*H*W,H,W], ..., level L-1].  ptlflow/models/raft/corr.py:13-27,56-64."""
+    require_cuda(fmap1, "fmap1"); require_cuda(fmap2, "fmap2")
+    if fmap1.shape != fmap2.shape or fmap1.dtype != fmap2.dtype or fmap1.dim() != 4:
+        raise RuntimeError("corr_volume_build: fmap1/fmap2 must be [B,H,W,C] with equal shape and dtype")
+    B, H, W, Cc = fmap1.shape
+    if (H >> (levels - 1)) < 1 or (W >> (levels - 1)) < 1:
+        raise RuntimeError(f"corr_volume_build: {H}x{W} grid too small for {levels} levels")
+    pyr = list(out) if out is not None else alloc_pyramid(B, H, W, levels, fmap1.dtype, fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        check(load().pfb_corr_volume_build(fmap1.data_ptr(), fmap2.data_ptr(), ptr_array(pyr), B, H, W, Cc, levels,
+                                           dtype_code(fmap1.dtype), impl, stream_ptr(fmap1.device)), "corr_volume_build")
+    return pyr
+
+
+# ------------------------------------------------------------------------------------------
+# a3
+# ------------------------------------------------------------------------------------------
+def corr_lookup(pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: int, grid_hw, nchw: bool = True,
+                out_dtype: Optional[torch.dtype] = None, out_stride: Optional[int] = None) -> torch.Tensor:
+    """coords fp32 [B,H,W,2] -> [B, L*(2r+1)^2, H, W] (nchw) or [B,H,W,out_stride].  corr.py:29-54."""
+    require_cuda(coords, "coords")
+    if coords.dtype != torch.float32:
+        raise RuntimeError("corr_lookup: coords must be float32 [B,H,W,2]")
+    B, H, W, _ = coords.shape
+    assert (H, W) == tuple(grid_hw)
+    L = len(pyramid)
+    planes = L * (2 * radius + 1) ** 2
+    odt = out_dtype or pyramid[0].dtype
+    stride = planes if out_stride is None else out_stride
+    out = torch.empty((B, planes, H, W) if nchw else (B, H, W, stride), dtype=odt, device=coords.device)
+    with torch.cuda.device(coords.device):
+        check(load().pfb_corr_lookup(ptr_array(pyramid), coords.data_ptr(), out.data_ptr(), B, H, W, L, radius,
+                                     dtype_code(pyramid[0].dtype), dtype_code(odt), int(nchw), stride,
+                                     stream_ptr(coords.device)), "corr_lookup")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# a4
+# ------------------------------------------------------------------------------------------
+def avg_pool2x2(x: torch.Tensor) -> torch.Tensor:
+    """[N,H,W,C] -> [N,H/2,W/2,C]."""
+    require_cuda(x, "x")
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, H // 2, W // 2, Cc), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().pfb_avg_pool2x2_nhwc(x.data_ptr(), out.data_ptr(), N, H, W, Cc, dtype_code(x.dtype), stream_ptr(x.device)), "avg_pool2x2")
+    return out
+
+
+def feature_pyramid(fmap2: torch.Tensor, levels: int) -> List[torch.Tensor]:
+    """fmap2 [B,H,W,C] and its pooled copies (AlternateCorrBlock.__init__, corr.py:67-76)."""
+    pyr = [fmap2]
+    for _ in range(levels - 1):
+        pyr.append(avg_pool2x2(pyr[-1]))
+    return pyr
+
+
+def corr_lookup_onthefly(fmap1: torch.Tensor, fmap2_pyramid: Sequence[torch.Tensor], coords: torch.Tensor,
+                         radius: int, nchw: bool = True, out_dtype: Optional[torch.dtype] = None,
+                         out_stride: Optional[int] = None) -> torch.Tensor:
+    require_cuda(fmap1, "fmap1"); require_cuda(coords, "coords")
+    B, H, W, Cc = fmap1.shape
+    L = len(fmap2_pyramid)
+    planes = L * (2 * radius + 1) ** 2
+    odt = out_dtype or fmap1.dtype
+    stride = planes if out_stride is None else out_stride
+    out = torch.empty((B, planes, H, W) if nchw else (B, H, W, stride), dtype=odt, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        check(load().pfb_corr_lookup_onthefly(fmap1.data_ptr(), ptr_array(fmap2_pyramid), coords.data_ptr(), out.data_ptr(),
+                                              B, H, W, Cc, L, radius, dtype_code(fmap1.dtype), dtype_code(odt), int(nchw),
+                                              stride, stream_ptr(fmap1.device)), "corr_lookup_onthefly")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# conv building block
+# ------------------------------------------------------------------------------------------
+class PackedConv:
+    """One (possibly fused) conv layer: packed weight [KH*KW][Cin][Cout_pad] + fp32 bias."""
+
+    def __init__(self, convs, dtype: torch.dtype, device, cout_align: int = 8):
+        convs = list(convs)
+        w0 = convs[0].weight
+        self.Cin, self.KH, self.KW = w0.shape[1], w0.shape[2], w0.shape[3]
+        for c in convs:
+            assert tuple(c.weight.shape[1:]) == (self.Cin, self.KH, self.KW)
+        self.Cout = sum(c.weight.shape[0] for c in convs)
+        self.Cout_pad = (self.Cout + cout_align - 1) // cout_align * cout_align
+        self.dtype = dtype
+        self.weight = torch.zeros((self.KH * self.KW, self.Cin, self.Cout_pad), dtype=dtype, device=device)
+        self.bias = torch.zeros((self.Cout_pad,), dtype=torch.float32, device=device)
+        lib = load()
+        off = 0
+        with torch.cuda.device(device):
+            for c in convs:
+                w = c.weight.detach().to(device).contiguous()
+                check(lib.pfb_pack_conv_weight(w.data_ptr(), self.weight.data_ptr(), w.shape[0], self.Cin, self.KH, self.KW,
+                                               self.Cout_pad, off, dtype_code(w.dtype), dtype_code(dtype), stream_ptr(device)), "pack_conv_weight")
+                if c.bias is not None:
+                    bsrc = c.bias.detach().to(device).contiguous()
+                    check(lib.pfb_pack_bias(bsrc.data_ptr(), self.bias.data_ptr(), bsrc.numel(), off, dtype_code(bsrc.dtype), stream_ptr(device)), "pack_bias")
+                off += w.shape[0]
+                # keep sources alive until the (async) kernels are enqueued on the same stream: they are
+                self._keep = (w,)
+
+    def layer_struct(self) -> _lib.Layer:
+        return _lib.Layer(self.weight.data_ptr(), self.bias.data_ptr(), self.Cout, self.Cout_pad, self.Cin, self.KH, self.KW)
+
+
+def conv2d(srcs, packed: PackedConv, out: torch.Tensor, epilogue: int = _lib.EPI_LINEAR, out_offset: int = 0,
+           scale: float = 1.0, aux_h=None, aux_z=None, hidden: int = 0, coords=None, flow=None, impl: int = 0) -> torch.Tensor:
+    """srcs: list of tensors [B,H,W,Ci] or (tensor, channels, offset) triples.  Mostly for tests."""
+    p = _lib.ConvParams()
+    first = srcs[0][0] if isinstance(srcs[0], tuple) else srcs[0]
+    B, H, W = first.shape[:3]
+    for i, s in enumerate(srcs):
+        t, ch, off = s if isinstance(s, tuple) else (s, s.shape[-1], 0)
+        require_cuda(t, f"src{i}")
+        p.src[i] = _lib.ConvSrc(t.data_ptr(), ch, t.shape[-1], off, int(t.dtype == torch.float32 and packed.dtype != torch.float32))
+    p.nsrc = len(srcs)
+    p.B, p.H, p.W, p.KH, p.KW = B, H, W, packed.KH, packed.KW
+    p.Cout, p.Cout_pad = packed.Cout, packed.Cout_pad
+    p.weight, p.bias = packed.weight.data_ptr(), packed.bias.data_ptr()
+    p.epilogue, p.scale = epilogue, scale
+    p.out, p.out_stride, p.out_offset = out.data_ptr(), out.shape[-1], out_offset
+    p.aux_h = aux_h.data_ptr() if aux_h is not None else None
+    p.aux_z = aux_z.data_ptr() if aux_z is not None else None
+    p.hidden = hidden
+    p.coords = coords.data_ptr() if coords is not None else None
+    p.flow = flow.data_ptr() if flow is not None else None
+    p.dtype, p.impl = dtype_code(packed.dtype), impl
+    with torch.cuda.device(out.device):
+        check(load().pfb_conv2d(C.byref(p), stream_ptr(out.device)), "conv2d")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# a10 and small helpers
+# ------------------------------------------------------------------------------------------
+def convex_upsample(coords: torch.Tensor, mask: torch.Tensor, out_hw=None, pad=(0, 0)):
+    """coords fp32 [B,H,W,2], mask [B,H,W,576] -> (flow_up fp32 [B,2,oh,ow], flow_small fp32 [B,2,H,W])."""
+    require_cuda(coords, "coords"); require_cuda(mask, "mask")
+    B, H, W, _ = coords.shape
+    oh, ow = out_hw or (8 * H, 8 * W)
+    up = torch.empty((B, 2, oh, ow), dtype=torch.float32, device=coords.device)
+    small = torch.empty((B, 2, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        check(load().pfb_convex_upsample(coords.data_ptr(), mask.data_ptr(), up.data_ptr(), small.data_ptr(), B, H, W, oh, ow,
+                                         pad[0], pad[1], dtype_code(mask.dtype), stream_ptr(coords.device)), "convex_upsample")
+    return up, small
+
+
+def upflow8(coords: torch.Tensor, out_hw=None, pad=(0, 0)):
+    require_cuda(coords, "coords")
+    B, H, W, _ = coords.shape
+    oh, ow = out_hw or (8 * H, 8 * W)
+    up = torch.empty((B, 2, oh, ow), dtype=torch.float32, device=coords.device)
+    small = torch.empty((B, 2, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        check(load().pfb_upflow8(coords.data_ptr(), up.data_ptr(), small.data_ptr(), B, H, W, oh, ow, pad[0], pad[1],
+                                 stream_ptr(coords.device)), "upflow8")
+    return up, small
+
+
+def init_coords(B: int, H: int, W: int, device, flow_init: Optional[torch.Tensor] = None) -> torch.Tensor:
+    coords = torch.empty((B, H, W, 2), dtype=torch.float32, device=device)
+    fi = None
+    if flow_init is not None:
+        fi = flow_init.to(device=device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(device):
+        check(load().pfb_init_coords(coords.data_ptr(), fi.data_ptr() if fi is not None else None, B, H, W, stream_ptr(device)), "init_coords")
+    return coords
+
+
+def context_split(cnet: torch.Tensor, hidden: int, context: int):
+    """cnet [B,H,W,hidden+context] -> (tanh(net), relu(inp)) pixel-major.  raft.py:155-158."""
+    require_cuda(cnet, "cnet")
+    B, H, W, Cc = cnet.shape
+    assert Cc == hidden + context
+    net = torch.empty((B, H, W, hidden), dtype=cnet.dtype, device=cnet.device)
+    inp = torch.empty((B, H, W, context), dtype=cnet.dtype, device=cnet.device)
+    with torch.cuda.device(cnet.device):
+        check(load().pfb_context_split(cnet.data_ptr(), net.data_ptr(), inp.data_ptr(), B, H, W, hidden, context,
+                                       dtype_code(cnet.dtype), stream_ptr(cnet.device)), "context_split")
+    return net, inp
