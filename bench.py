@@ -33,6 +33,30 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+T_START = time.time()
+
+
+def log(msg: str) -> None:
+    """Progress on stderr (the JSON result line is the only thing written to stdout)."""
+    print(f"[bench +{time.time() - T_START:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def host_cores() -> int:
+    """Cores this process may really use: min(cpu_count, affinity mask, cgroup cpu.max quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -191,10 +215,12 @@ def run_ours(args):
         host_out.copy_(out["flows"], non_blocking=True)
         return out
 
+    log(f"model on {dev}, {args.dtype}, batch {B}; warming up")
     with torch.no_grad():
         for i in range(max(3, args.warmup)):
             step_resident(i)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            log(f"warm-up step {i} done")
 
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -210,6 +236,7 @@ def run_ours(args):
         torch.cuda.synchronize(); sharding.barrier()
         launches = lib.pfb_launch_count(-1) - n0
         ms_value = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        log(f"resident: {ms_value / args.steps:.2f} ms/step")
 
         # ---- e2e: pinned host inputs, H2D + forward + D2H of the flow every step ----
         for i in range(2):
@@ -225,6 +252,7 @@ def run_ours(args):
         sharding.barrier()
         ms_e2e = sharding.max_over_ranks(max(e0.elapsed_time(e1), wall_ms), dev)
         clocks = sampler.stop()
+        log(f"e2e: {ms_e2e / args.steps:.2f} ms/step; clocks {clocks}")
 
         # ---- instrumented pass: live per-kernel-class durations (not part of the numbers above) ----
         prof_steps = 2
@@ -234,6 +262,7 @@ def run_ours(args):
         ms_arr, n_arr = (C.c_double * 8)(), (C.c_ulonglong * 8)()
         _lib.check(lib.pfb_profile_collect(ms_arr, n_arr, 8), "profile_collect")
         lib.pfb_profile_enable(0)
+        log("instrumented pass done")
 
     H8, W8 = (H + 7) // 8, (W + 7) // 8
     esize = 4 if dtype == torch.float32 else 2
@@ -301,8 +330,9 @@ def _cpu_setup(args):
     from oracle import raft_oracle as O
     from oracle import synth
 
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
+    log(f"cpu arm: {cores} host threads (os.cpu_count()={os.cpu_count()})")
     sd = synth.synth_state_dict(O.state_dict_shapes(args.model), 1234)
     g = torch.Generator().manual_seed(7)
 
@@ -316,13 +346,17 @@ def _cpu_setup(args):
 
 def cpu_baseline(args, budget_s: float):
     one_pair, cores = _cpu_setup(args)
-    one_pair()  # warm-up
-    n, t0 = 0, time.perf_counter()
-    while True:
-        one_pair(); n += 1
-        dt = time.perf_counter() - t0
-        if dt >= budget_s or n >= 16:
-            break
+    t0 = time.perf_counter()
+    one_pair()  # warm-up (counted only if it alone exhausts the budget)
+    n, dt = 1, time.perf_counter() - t0
+    log(f"cpu baseline warm-up pair took {dt:.2f}s")
+    if dt < budget_s:
+        n, t0 = 0, time.perf_counter()
+        while True:
+            one_pair(); n += 1
+            dt = time.perf_counter() - t0
+            if dt >= budget_s or n >= 16:
+                break
     return {"value": round(n / dt, 4), "unit": "pairs/s", "cores": cores, "kind": "port",
             "sample": f"{n} single frame pairs of the same workload ({args.model} {args.width}x{args.height}, {args.iters} iters, fp32, batch 1), oracle/raft_oracle.py on torch CPU"}
 
