@@ -150,6 +150,10 @@ typedef struct {
   const float* flow;   /* PFB_EPI_RELU_APPEND_FLOW: [B,H,W,2] fp32 */
   pfb_dtype dtype;
   int impl;            /* 0 auto, 1 SIMT, 2 tcgen05 */
+  /* tensor-core operand (f16/bf16 only, may be NULL -> SIMT path): the same weights packed K-major
+   * by pfb_pack_conv_weight_kmajor: [KH*KW][Cout_pad_k][Cin_pad], every source padded to 64 channels */
+  const void* weight_k;
+  int Cin_pad, Cout_pad_k;
 } pfb_conv_params;
 
 PFB_API int pfb_conv2d(const pfb_conv_params* p, pfb_stream stream);
@@ -161,6 +165,12 @@ PFB_API int pfb_pack_conv_weight(const void* src, void* dst, int Cout, int Cin, 
                          int col_offset, pfb_dtype src_dtype, pfb_dtype dst_dtype, pfb_stream stream);
 /* dst[offset + i] = (float) src[i] */
 PFB_API int pfb_pack_bias(const void* src, float* dst, int n, int offset, pfb_dtype src_dtype, pfb_stream stream);
+/* torch-layout weight -> K-major packing for the tcgen05 path: dst[tap][row_offset + co][kpos(ci)] where the
+ * input channels are the concatenation of `nsrc` sources of src_channels[i] channels and each source is
+ * padded to a multiple of 64 in dst (kpos skips the pad).  dst is [KH*KW][Cout_pad_k][Cin_pad]; zero it first. */
+PFB_API int pfb_pack_conv_weight_kmajor(const void* src, void* dst, int Cout, int Cin, int KH, int KW, int Cout_pad_k,
+                                        int row_offset, const int* src_channels, int nsrc, int Cin_pad,
+                                        pfb_dtype src_dtype, pfb_dtype dst_dtype, pfb_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * a10: upsampling
@@ -198,6 +208,8 @@ typedef struct {
   const void* weight; /* packed, see pfb_pack_conv_weight */
   const float* bias;
   int Cout, Cout_pad, Cin, KH, KW;
+  const void* weight_k; /* K-major packing (tcgen05), NULL if not packed */
+  int Cin_pad, Cout_pad_k;
 } pfb_layer;
 
 typedef struct {

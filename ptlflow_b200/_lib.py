@@ -42,12 +42,14 @@ class ConvParams(C.Structure):
         ("aux_h", C.c_void_p), ("aux_z", C.c_void_p), ("hidden", C.c_int),
         ("coords", C.c_void_p), ("flow", C.c_void_p),
         ("dtype", C.c_int), ("impl", C.c_int),
+        ("weight_k", C.c_void_p), ("Cin_pad", C.c_int), ("Cout_pad_k", C.c_int),
     ]
 
 
 class Layer(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("Cout", C.c_int), ("Cout_pad", C.c_int),
-                ("Cin", C.c_int), ("KH", C.c_int), ("KW", C.c_int)]
+                ("Cin", C.c_int), ("KH", C.c_int), ("KW", C.c_int),
+                ("weight_k", C.c_void_p), ("Cin_pad", C.c_int), ("Cout_pad_k", C.c_int)]
 
 
 class RaftCfg(C.Structure):
@@ -89,6 +91,7 @@ SIGNATURES = {
     "pfb_conv2d": (_I, [C.POINTER(ConvParams), _S]),
     "pfb_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_pack_bias": (_I, [_P, _P, _I, _I, _I, _S]),
+    "pfb_pack_conv_weight_kmajor": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int), _I, _I, _I, _I, _S]),
     "pfb_convex_upsample": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_upflow8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_context_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),

@@ -96,6 +96,11 @@ int conv2d_simt(const pfb_conv_params* p, cudaStream_t s);
 // conv_umma.cu (tcgen05); returns PFB_ERR_UNSUPPORTED when the shape does not fit
 int conv2d_umma(const pfb_conv_params* p, cudaStream_t s);
 bool conv2d_umma_supported(const pfb_conv_params* p);
+// conv_special.cu
+bool conv_cout2_supported(const pfb_conv_params* p);
+int conv_cout2_flow(const pfb_conv_params* p, cudaStream_t s);
+bool conv_flow7x7_supported(const pfb_conv_params* p);
+int conv_flow7x7(const pfb_conv_params* p, cudaStream_t s);
 // corr_umma.cu
 int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, int H, int W, int C, int L,
                      pfb_dtype dt, cudaStream_t s);

@@ -223,11 +223,14 @@ extern "C" PFB_API int pfb_conv2d(const pfb_conv_params* p, pfb_stream stream) {
       return PFB_ERR_ARG;
   }
   cudaStream_t s = as_stream(stream);
-  const bool can = conv2d_umma_supported(p);
-  if (p->impl == 2 && !can) {
-    set_error("conv2d: tcgen05 path does not support this shape/dtype");
-    return PFB_ERR_UNSUPPORTED;
+  if (p->impl != 1) {
+    if (conv_cout2_supported(p)) return conv_cout2_flow(p, s);
+    if (conv_flow7x7_supported(p)) return conv_flow7x7(p, s);
+    if (conv2d_umma_supported(p)) return conv2d_umma(p, s);
+    if (p->impl == 2) {
+      set_error("conv2d: tcgen05 path does not support this shape/dtype");
+      return PFB_ERR_UNSUPPORTED;
+    }
   }
-  if ((p->impl == 0 && can) || p->impl == 2) return conv2d_umma(p, s);
   return conv2d_simt(p, s);
 }

@@ -1,0 +1,230 @@
+// Two small convolutions of the update block that do not fit the tensor-core tile economically, plus
+// the K-major weight packing used by the tcgen05 path.
+//   * flow-head conv2 (3x3, 256 -> 2, update.py:9) fused with the coordinate update of raft.py:174-178:
+//     one warp per pixel, lanes split the input channels with 128-bit loads, shuffle reduction.
+//   * motion-encoder convf1 (7x7, 2 -> 128/64, update.py:99,:81): one thread per output channel keeps its
+//     98 weights in registers and slides a 16-pixel accumulator row over a shared-memory flow patch.
+#include "common.cuh"
+
+namespace pfb {
+
+template <typename T>
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+  const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = to_f32(h[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_cout2_flow_kernel(const T* __restrict__ x, int stride, int offset, int Cin,
+                                                              int B, int H, int W, int KH, int KW,
+                                                              const T* __restrict__ wk, int Cout_pad_k, int Cin_pad,
+                                                              const float* __restrict__ bias, float* __restrict__ coords,
+                                                              float* __restrict__ flow_out) {
+  const int P = B * H * W;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= P) return;
+  const int px = p % W, py = (p / W) % H, b = p / (W * H);
+  const int ph = KH >> 1, pw = KW >> 1;
+  float a0 = 0.f, a1 = 0.f;
+  for (int tap = 0; tap < KH * KW; ++tap) {
+    const int iy = py + tap / KW - ph, ix = px + tap % KW - pw;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;  // warp-uniform
+    const T* xp = x + ((size_t)(b * H + iy) * W + ix) * stride + offset;
+    const T* w0 = wk + (size_t)(tap * Cout_pad_k) * Cin_pad;
+    const T* w1 = w0 + Cin_pad;
+    for (int c8 = lane; c8 < Cin / 8; c8 += 32) {
+      float xf[8], f0[8], f1[8];
+      unpack8f<T>(__ldg(reinterpret_cast<const uint4*>(xp) + c8), xf);
+      unpack8f<T>(__ldg(reinterpret_cast<const uint4*>(w0) + c8), f0);
+      unpack8f<T>(__ldg(reinterpret_cast<const uint4*>(w1) + c8), f1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a0 = fmaf(xf[e], f0[e], a0);
+        a1 = fmaf(xf[e], f1[e], a1);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (lane == 0) {
+    const float c0 = coords[2 * (size_t)p] + a0 + (bias ? bias[0] : 0.f);
+    const float c1 = coords[2 * (size_t)p + 1] + a1 + (bias ? bias[1] : 0.f);
+    coords[2 * (size_t)p] = c0;
+    coords[2 * (size_t)p + 1] = c1;
+    flow_out[2 * (size_t)p] = c0 - (float)px;
+    flow_out[2 * (size_t)p + 1] = c1 - (float)py;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kFTH = 8, kFTW = 16;  // pixel tile of the 7x7 flow conv
+
+template <typename T>
+__global__ void __launch_bounds__(128) conv_flow7x7_kernel(const float* __restrict__ flow, int B, int H, int W,
+                                                           const T* __restrict__ w /*[49][2][Cout_pad]*/, int Cout,
+                                                           int Cout_pad, const float* __restrict__ bias,
+                                                           T* __restrict__ out, int out_stride, int out_offset) {
+  __shared__ float patch[kFTH + 6][kFTW + 6][2];
+  const int PW = (W + kFTW - 1) / kFTW, PH = (H + kFTH - 1) / kFTH;
+  int t = blockIdx.x;
+  const int pw = t % PW;
+  t /= PW;
+  const int ph = t % PH;
+  const int b = t / PH;
+  const int x0 = pw * kFTW, y0 = ph * kFTH;
+  for (int i = threadIdx.x; i < (kFTH + 6) * (kFTW + 6); i += blockDim.x) {
+    const int r = i / (kFTW + 6), c = i - r * (kFTW + 6);
+    const int y = y0 + r - 3, x = x0 + c - 3;
+    float fx = 0.f, fy = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const float2 f = *reinterpret_cast<const float2*>(flow + 2 * ((size_t)(b * H + y) * W + x));
+      fx = f.x;
+      fy = f.y;
+    }
+    patch[r][c][0] = fx;
+    patch[r][c][1] = fy;
+  }
+  __syncthreads();
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  if (n >= Cout) return;
+  float wr[49][2];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) {
+    wr[k][0] = to_f32(w[(size_t)(k * 2 + 0) * Cout_pad + n]);
+    wr[k][1] = to_f32(w[(size_t)(k * 2 + 1) * Cout_pad + n]);
+  }
+  const float bn = bias ? bias[n] : 0.f;
+  for (int ry = 0; ry < kFTH; ++ry) {
+    const int y = y0 + ry;
+    if (y >= H) break;
+    float acc[kFTW];
+#pragma unroll
+    for (int i = 0; i < kFTW; ++i) acc[i] = bn;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+      for (int ix = 0; ix < kFTW + 6; ++ix) {
+        const float vx = patch[ry + ky][ix][0], vy = patch[ry + ky][ix][1];
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int ox = ix - kx;
+          if (ox >= 0 && ox < kFTW) acc[ox] = fmaf(wr[ky * 7 + kx][1], vy, fmaf(wr[ky * 7 + kx][0], vx, acc[ox]));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kFTW; ++i) {
+      const int x = x0 + i;
+      if (x < W) out[((size_t)(b * H + y) * W + x) * out_stride + out_offset + n] = from_f32<T>(fmaxf(acc[i], 0.f));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SrcSplit {
+  int n;
+  int ch[PFB_MAX_SRC];
+};
+
+__global__ void pack_kmajor_kernel(const void* __restrict__ src, void* __restrict__ dst, int Cout, int Cin, int KH, int KW,
+                                   int Cout_pad_k, int row_offset, SrcSplit split, int Cin_pad, int sdt, int ddt) {
+  const size_t total = (size_t)Cout * Cin * KH * KW;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int ci = (int)(idx % Cin);
+    size_t t = idx / Cin;
+    int co = (int)(t % Cout);
+    int tap = (int)(t / Cout);
+    // position of input channel ci when every source is padded to a multiple of 64
+    int kpos = 0, rem = ci;
+    for (int s = 0; s < split.n; ++s) {
+      if (rem < split.ch[s]) { kpos += rem; break; }
+      rem -= split.ch[s];
+      kpos += (split.ch[s] + 63) / 64 * 64;
+    }
+    float v = load_as_f32(src, ((size_t)co * Cin + ci) * KH * KW + tap, sdt);
+    store_from_f32(dst, ((size_t)tap * Cout_pad_k + row_offset + co) * Cin_pad + kpos, ddt, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+bool conv_cout2_supported(const pfb_conv_params* p) {
+  if (p->dtype == PFB_F32 || p->epilogue != PFB_EPI_FLOW || p->Cout != 2 || !p->weight_k) return false;
+  if (p->nsrc != 1 || p->src[0].is_f32) return false;
+  const pfb_conv_src& s = p->src[0];
+  return s.channels % 8 == 0 && s.offset % 8 == 0 && s.stride % 8 == 0 && p->Cin_pad % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(s.ptr) & 15) == 0 && p->Cout_pad_k >= 2;
+}
+
+int conv_cout2_flow(const pfb_conv_params* p, cudaStream_t s) {
+  const int P = p->B * p->H * p->W;
+  const pfb_conv_src& x = p->src[0];
+  ProfScope prof(KC_CONV, s);
+  if (p->dtype == PFB_F16)
+    conv_cout2_flow_kernel<__half><<<ceil_div(P, 8), 256, 0, s>>>((const __half*)x.ptr, x.stride, x.offset, x.channels, p->B, p->H,
+                                                                  p->W, p->KH, p->KW, (const __half*)p->weight_k, p->Cout_pad_k,
+                                                                  p->Cin_pad, p->bias, p->coords, (float*)p->out);
+  else
+    conv_cout2_flow_kernel<__nv_bfloat16><<<ceil_div(P, 8), 256, 0, s>>>((const __nv_bfloat16*)x.ptr, x.stride, x.offset, x.channels,
+                                                                         p->B, p->H, p->W, p->KH, p->KW,
+                                                                         (const __nv_bfloat16*)p->weight_k, p->Cout_pad_k,
+                                                                         p->Cin_pad, p->bias, p->coords, (float*)p->out);
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}
+
+bool conv_flow7x7_supported(const pfb_conv_params* p) {
+  return p->dtype != PFB_F32 && p->nsrc == 1 && p->src[0].is_f32 && p->src[0].channels == 2 && p->src[0].stride == 2 &&
+         p->src[0].offset == 0 && p->KH == 7 && p->KW == 7 && p->epilogue == PFB_EPI_RELU;
+}
+
+int conv_flow7x7(const pfb_conv_params* p, cudaStream_t s) {
+  dim3 grid(ceil_div(p->W, kFTW) * ceil_div(p->H, kFTH) * p->B, ceil_div(p->Cout, 128));
+  ProfScope prof(KC_CONV, s);
+  if (p->dtype == PFB_F16)
+    conv_flow7x7_kernel<__half><<<grid, 128, 0, s>>>((const float*)p->src[0].ptr, p->B, p->H, p->W, (const __half*)p->weight, p->Cout,
+                                                     p->Cout_pad, p->bias, (__half*)p->out, p->out_stride, p->out_offset);
+  else
+    conv_flow7x7_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>((const float*)p->src[0].ptr, p->B, p->H, p->W, (const __nv_bfloat16*)p->weight,
+                                                            p->Cout, p->Cout_pad, p->bias, (__nv_bfloat16*)p->out, p->out_stride,
+                                                            p->out_offset);
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}
+
+}  // namespace pfb
+
+using namespace pfb;
+
+extern "C" PFB_API int pfb_pack_conv_weight_kmajor(const void* src, void* dst, int Cout, int Cin, int KH, int KW,
+                                                   int Cout_pad_k, int row_offset, const int* src_channels, int nsrc,
+                                                   int Cin_pad, pfb_dtype src_dtype, pfb_dtype dst_dtype, pfb_stream stream) {
+  PFB_CHECK_ARG(src && dst && src_channels, "pack_conv_weight_kmajor: null pointer");
+  PFB_CHECK_ARG(dtype_ok(src_dtype) && dtype_ok(dst_dtype), "pack_conv_weight_kmajor: bad dtype");
+  PFB_CHECK_ARG(nsrc >= 1 && nsrc <= PFB_MAX_SRC, "pack_conv_weight_kmajor: nsrc=%d", nsrc);
+  PFB_CHECK_ARG(Cout > 0 && Cin > 0 && KH > 0 && KW > 0 && row_offset >= 0 && row_offset + Cout <= Cout_pad_k,
+                "pack_conv_weight_kmajor: bad shape");
+  SrcSplit sp{};
+  sp.n = nsrc;
+  int sum = 0, padded = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    PFB_CHECK_ARG(src_channels[i] > 0, "pack_conv_weight_kmajor: source %d has %d channels", i, src_channels[i]);
+    sp.ch[i] = src_channels[i];
+    sum += src_channels[i];
+    padded += (src_channels[i] + 63) / 64 * 64;
+  }
+  PFB_CHECK_ARG(sum == Cin && padded == Cin_pad, "pack_conv_weight_kmajor: sources sum to %d (pad %d), expected Cin=%d Cin_pad=%d", sum,
+                padded, Cin, Cin_pad);
+  size_t total = (size_t)Cout * Cin * KH * KW;
+  unsigned blocks = (unsigned)(ceil_div_sz(total, 256) > 4096 ? 4096 : ceil_div_sz(total, 256));
+  ProfScope prof(KC_MISC, as_stream(stream));
+  pack_kmajor_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, dst, Cout, Cin, KH, KW, Cout_pad_k, row_offset, sp, Cin_pad,
+                                                            (int)src_dtype, (int)dst_dtype);
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}

@@ -100,6 +100,7 @@ static int run_conv(const Ctx& x, int layer, std::initializer_list<pfb_conv_src>
   p.aux_h = x.b->net; p.aux_z = x.at(x.ws.off_z); p.hidden = x.c->hidden_dim;
   p.coords = x.b->coords; p.flow = reinterpret_cast<const float*>(x.at(x.ws.off_flow));
   p.dtype = x.c->dtype; p.impl = x.c->impl;
+  p.weight_k = L.weight_k; p.Cin_pad = L.Cin_pad; p.Cout_pad_k = L.Cout_pad_k;
   return pfb_conv2d(&p, (pfb_stream)x.s);
 }
 

@@ -27,25 +27,36 @@ class RaftEngine:
         self.dtype, self.device, self.impl = dtype, device, impl
         ub = update_block
         enc, gru, fh = ub.encoder, ub.gru, ub.flow_head
-        P = lambda *convs: ops.PackedConv(convs, dtype, device)  # noqa: E731
+        planes = corr_levels * (2 * corr_radius + 1) ** 2
+        hd, cd = hidden_dim, context_dim
+
+        def P(srcs, *convs):  # srcs: channel counts of the concatenated inputs, in order (tcgen05 K-major pack)
+            return ops.PackedConv(convs, dtype, device, src_channels=srcs)
+
         layers: Dict[int, ops.PackedConv] = {}
-        layers[_lib.L_CONVC1] = P(enc.convc1)
-        layers[_lib.L_CONVF1] = P(enc.convf1)
-        layers[_lib.L_CONVF2] = P(enc.convf2)
-        layers[_lib.L_CONV] = P(enc.conv)
-        layers[_lib.L_FLOW1] = P(fh.conv1)
-        layers[_lib.L_FLOW2] = P(fh.conv2)
+        layers[_lib.L_CONVF1] = P(None, enc.convf1)  # 7x7 on the 2-channel fp32 flow: dedicated kernel
         if variant == 0:
-            layers[_lib.L_CONVC2] = P(enc.convc2)
-            layers[_lib.L_GRU_ZR1] = P(gru.convz1, gru.convr1)  # z | r share the input: one GEMM, N = 2*hidden
-            layers[_lib.L_GRU_Q1] = P(gru.convq1)
-            layers[_lib.L_GRU_ZR2] = P(gru.convz2, gru.convr2)
-            layers[_lib.L_GRU_Q2] = P(gru.convq2)
-            layers[_lib.L_MASK1] = P(ub.mask[0])
-            layers[_lib.L_MASK2] = P(ub.mask[2])
-        else:
-            layers[_lib.L_GRU_ZR1] = P(gru.convz, gru.convr)
-            layers[_lib.L_GRU_Q1] = P(gru.convq)
+            layers[_lib.L_CONVC1] = P([planes], enc.convc1)
+            layers[_lib.L_CONVC2] = P([256], enc.convc2)
+            layers[_lib.L_CONVF2] = P([128], enc.convf2)
+            layers[_lib.L_CONV] = P([256], enc.conv)  # cat[cor(192), flo(64)] lives in one 256-channel buffer
+            gsrc = [hd, cd, 128]  # cat[h or r*h, inp, motion] -- three tensor maps, no concat copy
+            layers[_lib.L_GRU_ZR1] = P(gsrc, gru.convz1, gru.convr1)  # z | r share the input: one GEMM, N = 2*hidden
+            layers[_lib.L_GRU_Q1] = P(gsrc, gru.convq1)
+            layers[_lib.L_GRU_ZR2] = P(gsrc, gru.convz2, gru.convr2)
+            layers[_lib.L_GRU_Q2] = P(gsrc, gru.convq2)
+            layers[_lib.L_FLOW1] = P([hd], fh.conv1)
+            layers[_lib.L_FLOW2] = P([256], fh.conv2)
+            layers[_lib.L_MASK1] = P([hd], ub.mask[0])
+            layers[_lib.L_MASK2] = P([256], ub.mask[2])
+        else:  # raft_small: odd channel counts (96 / 82 / 146) -> SIMT kernels only
+            layers[_lib.L_CONVC1] = P(None, enc.convc1)
+            layers[_lib.L_CONVF2] = P(None, enc.convf2)
+            layers[_lib.L_CONV] = P(None, enc.conv)
+            layers[_lib.L_GRU_ZR1] = P(None, gru.convz, gru.convr)
+            layers[_lib.L_GRU_Q1] = P(None, gru.convq)
+            layers[_lib.L_FLOW1] = P(None, fh.conv1)
+            layers[_lib.L_FLOW2] = P(None, fh.conv2)
         self.layers = layers
         self.weights = _lib.RaftWeights()
         for k, v in layers.items():

@@ -119,7 +119,9 @@ def corr_lookup_onthefly(fmap1: torch.Tensor, fmap2_pyramid: Sequence[torch.Tens
 class PackedConv:
     """One (possibly fused) conv layer: packed weight [KH*KW][Cin][Cout_pad] + fp32 bias."""
 
-    def __init__(self, convs, dtype: torch.dtype, device, cout_align: int = 8):
+    def __init__(self, convs, dtype: torch.dtype, device, cout_align: int = 8, src_channels=None):
+        """``src_channels`` (list of the concatenated sources' channel counts) additionally builds the K-major
+        packing [KH*KW][Cout_pad_k][Cin_pad] consumed by the tcgen05 kernels (f16 / bf16 only)."""
         convs = list(convs)
         w0 = convs[0].weight
         self.Cin, self.KH, self.KW = w0.shape[1], w0.shape[2], w0.shape[3]
@@ -129,7 +131,13 @@ class PackedConv:
         self.Cout_pad = (self.Cout + cout_align - 1) // cout_align * cout_align
         self.dtype = dtype
         self.weight = torch.zeros((self.KH * self.KW, self.Cin, self.Cout_pad), dtype=dtype, device=device)
-        self.bias = torch.zeros((self.Cout_pad,), dtype=torch.float32, device=device)
+        self.weight_k, self.Cin_pad, self.Cout_pad_k = None, 0, 0
+        if src_channels is not None and dtype != torch.float32:
+            assert sum(src_channels) == self.Cin
+            self.Cin_pad = sum((c + 63) // 64 * 64 for c in src_channels)
+            self.Cout_pad_k = (self.Cout + 31) // 32 * 32 if self.Cout >= 32 else 16
+            self.weight_k = torch.zeros((self.KH * self.KW, self.Cout_pad_k, self.Cin_pad), dtype=dtype, device=device)
+        self.bias = torch.zeros((max(self.Cout_pad, self.Cout_pad_k, 32),), dtype=torch.float32, device=device)
         lib = load()
         off = 0
         with torch.cuda.device(device):
@@ -137,15 +145,19 @@ class PackedConv:
                 w = c.weight.detach().to(device).contiguous()
                 check(lib.pfb_pack_conv_weight(w.data_ptr(), self.weight.data_ptr(), w.shape[0], self.Cin, self.KH, self.KW,
                                                self.Cout_pad, off, dtype_code(w.dtype), dtype_code(dtype), stream_ptr(device)), "pack_conv_weight")
+                if self.weight_k is not None:
+                    sc = (C.c_int * len(src_channels))(*src_channels)
+                    check(lib.pfb_pack_conv_weight_kmajor(w.data_ptr(), self.weight_k.data_ptr(), w.shape[0], self.Cin, self.KH, self.KW,
+                                                          self.Cout_pad_k, off, sc, len(src_channels), self.Cin_pad,
+                                                          dtype_code(w.dtype), dtype_code(dtype), stream_ptr(device)), "pack_conv_weight_kmajor")
                 if c.bias is not None:
                     bsrc = c.bias.detach().to(device).contiguous()
                     check(lib.pfb_pack_bias(bsrc.data_ptr(), self.bias.data_ptr(), bsrc.numel(), off, dtype_code(bsrc.dtype), stream_ptr(device)), "pack_bias")
                 off += w.shape[0]
-                # keep sources alive until the (async) kernels are enqueued on the same stream: they are
-                self._keep = (w,)
 
     def layer_struct(self) -> _lib.Layer:
-        return _lib.Layer(self.weight.data_ptr(), self.bias.data_ptr(), self.Cout, self.Cout_pad, self.Cin, self.KH, self.KW)
+        return _lib.Layer(self.weight.data_ptr(), self.bias.data_ptr(), self.Cout, self.Cout_pad, self.Cin, self.KH, self.KW,
+                          self.weight_k.data_ptr() if self.weight_k is not None else None, self.Cin_pad, self.Cout_pad_k)
 
 
 def conv2d(srcs, packed: PackedConv, out: torch.Tensor, epilogue: int = _lib.EPI_LINEAR, out_offset: int = 0,
@@ -170,6 +182,8 @@ def conv2d(srcs, packed: PackedConv, out: torch.Tensor, epilogue: int = _lib.EPI
     p.coords = coords.data_ptr() if coords is not None else None
     p.flow = flow.data_ptr() if flow is not None else None
     p.dtype, p.impl = dtype_code(packed.dtype), impl
+    p.weight_k = packed.weight_k.data_ptr() if packed.weight_k is not None else None
+    p.Cin_pad, p.Cout_pad_k = packed.Cin_pad, packed.Cout_pad_k
     with torch.cuda.device(out.device):
         check(load().pfb_conv2d(C.byref(p), stream_ptr(out.device)), "conv2d")
     return out
