@@ -16,49 +16,64 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+// Flow head conv2: the two weight rows of every tap are staged once per block in shared memory; each warp
+// then walks pixels (grid-stride), issuing the 128-bit loads of all taps before the FMAs.
+template <typename T, int KH, int KW>
 __global__ void __launch_bounds__(256) conv_cout2_flow_kernel(const T* __restrict__ x, int stride, int offset, int Cin,
-                                                              int B, int H, int W, int KH, int KW,
-                                                              const T* __restrict__ wk, int Cout_pad_k, int Cin_pad,
-                                                              const float* __restrict__ bias, float* __restrict__ coords,
-                                                              float* __restrict__ flow_out) {
+                                                              int B, int H, int W, const T* __restrict__ wk,
+                                                              int Cout_pad_k, int Cin_pad, const float* __restrict__ bias,
+                                                              float* __restrict__ coords, float* __restrict__ flow_out) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  T* sw = reinterpret_cast<T*>(sm_raw);  // [tap][2][Cin]
+  constexpr int TAPS = KH * KW;
+  const int c8n = Cin / 8;
+  for (int i = threadIdx.x; i < TAPS * 2 * c8n; i += blockDim.x) {
+    const int c8 = i % c8n, n = (i / c8n) & 1, tap = i / (2 * c8n);
+    reinterpret_cast<uint4*>(sw)[i] = __ldg(reinterpret_cast<const uint4*>(wk + ((size_t)tap * Cout_pad_k + n) * Cin_pad) + c8);
+  }
+  __syncthreads();
   const int P = B * H * W;
-  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (p >= P) return;
-  const int px = p % W, py = (p / W) % H, b = p / (W * H);
-  const int ph = KH >> 1, pw = KW >> 1;
-  float a0 = 0.f, a1 = 0.f;
-  for (int tap = 0; tap < KH * KW; ++tap) {
-    const int iy = py + tap / KW - ph, ix = px + tap % KW - pw;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;  // warp-uniform
-    const T* xp = x + ((size_t)(b * H + iy) * W + ix) * stride + offset;
-    const T* w0 = wk + (size_t)(tap * Cout_pad_k) * Cin_pad;
-    const T* w1 = w0 + Cin_pad;
-    for (int c8 = lane; c8 < Cin / 8; c8 += 32) {
-      float xf[8], f0[8], f1[8];
-      unpack8f<T>(__ldg(reinterpret_cast<const uint4*>(xp) + c8), xf);
-      unpack8f<T>(__ldg(reinterpret_cast<const uint4*>(w0) + c8), f0);
-      unpack8f<T>(__ldg(reinterpret_cast<const uint4*>(w1) + c8), f1);
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f;
+  for (int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < P; p += warps_total) {
+    const int px = p % W, py = (p / W) % H, b = p / (W * H);
+    float a0 = 0.f, a1 = 0.f;
+    for (int c8 = lane; c8 < c8n; c8 += 32) {
+      uint4 xv[TAPS];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        a0 = fmaf(xf[e], f0[e], a0);
-        a1 = fmaf(xf[e], f1[e], a1);
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const int iy = py + tap / KW - KH / 2, ix = px + tap % KW - KW / 2;
+        const bool inb = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        xv[tap] = inb ? __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + iy) * W + ix) * stride + offset) + c8)
+                      : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int tap = 0; tap < TAPS; ++tap) {
+        float xf[8], f0[8], f1[8];
+        unpack8f<T>(xv[tap], xf);
+        unpack8f<T>(reinterpret_cast<const uint4*>(sw)[(tap * 2 + 0) * c8n + c8], f0);
+        unpack8f<T>(reinterpret_cast<const uint4*>(sw)[(tap * 2 + 1) * c8n + c8], f1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a0 = fmaf(xf[e], f0[e], a0);
+          a1 = fmaf(xf[e], f1[e], a1);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-  }
-  if (lane == 0) {
-    const float c0 = coords[2 * (size_t)p] + a0 + (bias ? bias[0] : 0.f);
-    const float c1 = coords[2 * (size_t)p + 1] + a1 + (bias ? bias[1] : 0.f);
-    coords[2 * (size_t)p] = c0;
-    coords[2 * (size_t)p + 1] = c1;
-    flow_out[2 * (size_t)p] = c0 - (float)px;
-    flow_out[2 * (size_t)p + 1] = c1 - (float)py;
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) {
+      const float c0 = coords[2 * (size_t)p] + a0 + b0;
+      const float c1 = coords[2 * (size_t)p + 1] + a1 + b1;
+      coords[2 * (size_t)p] = c0;
+      coords[2 * (size_t)p + 1] = c1;
+      flow_out[2 * (size_t)p] = c0 - (float)px;
+      flow_out[2 * (size_t)p + 1] = c1 - (float)py;
+    }
   }
 }
 
@@ -155,25 +170,28 @@ __global__ void pack_kmajor_kernel(const void* __restrict__ src, void* __restric
 // ---------------------------------------------------------------------------------------------
 bool conv_cout2_supported(const pfb_conv_params* p) {
   if (p->dtype == PFB_F32 || p->epilogue != PFB_EPI_FLOW || p->Cout != 2 || !p->weight_k) return false;
-  if (p->nsrc != 1 || p->src[0].is_f32) return false;
+  if (p->nsrc != 1 || p->src[0].is_f32 || p->KH != 3 || p->KW != 3) return false;
   const pfb_conv_src& s = p->src[0];
-  return s.channels % 8 == 0 && s.offset % 8 == 0 && s.stride % 8 == 0 && p->Cin_pad % 8 == 0 &&
+  return s.channels % 8 == 0 && s.offset % 8 == 0 && s.stride % 8 == 0 && p->Cin_pad % 8 == 0 && s.channels <= 1024 &&
          (reinterpret_cast<uintptr_t>(s.ptr) & 15) == 0 && p->Cout_pad_k >= 2;
 }
 
 int conv_cout2_flow(const pfb_conv_params* p, cudaStream_t s) {
   const int P = p->B * p->H * p->W;
   const pfb_conv_src& x = p->src[0];
+  int blocks = ceil_div(P, 8);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)9 * 2 * x.channels * 2;
   ProfScope prof(KC_CONV, s);
   if (p->dtype == PFB_F16)
-    conv_cout2_flow_kernel<__half><<<ceil_div(P, 8), 256, 0, s>>>((const __half*)x.ptr, x.stride, x.offset, x.channels, p->B, p->H,
-                                                                  p->W, p->KH, p->KW, (const __half*)p->weight_k, p->Cout_pad_k,
-                                                                  p->Cin_pad, p->bias, p->coords, (float*)p->out);
+    conv_cout2_flow_kernel<__half, 3, 3><<<blocks, 256, smem, s>>>((const __half*)x.ptr, x.stride, x.offset, x.channels, p->B, p->H, p->W,
+                                                                   (const __half*)p->weight_k, p->Cout_pad_k, p->Cin_pad, p->bias,
+                                                                   p->coords, (float*)p->out);
   else
-    conv_cout2_flow_kernel<__nv_bfloat16><<<ceil_div(P, 8), 256, 0, s>>>((const __nv_bfloat16*)x.ptr, x.stride, x.offset, x.channels,
-                                                                         p->B, p->H, p->W, p->KH, p->KW,
-                                                                         (const __nv_bfloat16*)p->weight_k, p->Cout_pad_k,
-                                                                         p->Cin_pad, p->bias, p->coords, (float*)p->out);
+    conv_cout2_flow_kernel<__nv_bfloat16, 3, 3><<<blocks, 256, smem, s>>>((const __nv_bfloat16*)x.ptr, x.stride, x.offset, x.channels, p->B,
+                                                                          p->H, p->W, (const __nv_bfloat16*)p->weight_k, p->Cout_pad_k,
+                                                                          p->Cin_pad, p->bias, p->coords, (float*)p->out);
   PFB_LAUNCH_CHECK();
   return PFB_OK;
 }

@@ -9,8 +9,11 @@
 //   N tile : all (<= 256) output channels of the layer in one TMEM accumulator (z|r of the GRU = 256).
 //   K loop : (tap, source, 64-channel chunk); one pipeline stage = A box (16 KB) + weight tile (N x 128 B).
 //
-// CTA = 6 warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer / TMEM owner; one output tile per CTA, two CTAs
-// per SM (<= 256 TMEM columns and <= ~100 KB smem each) so one CTA's epilogue overlaps the other's MMAs.
+// Persistent CTAs (one per SM, 6 warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer / TMEM owner) walk the
+// output tiles round-robin.  The smem ring (4-8 stages, ~200 KB) runs continuously across tiles and the
+// accumulator is double-buffered in TMEM (2 x <=256 columns), so the epilogue of tile i overlaps the MMAs of
+// tile i+1 and the TMA producer never drains at a tile boundary.  The 128-pixel M tile is TW x TH with TW*TH = 128
+// chosen per shape to minimise padding (128x1 rows for W = 128: 440 tiles = 2.97 waves of 148 SMs).
 // The epilogue fuses bias + ReLU / sigmoid / tanh + the GRU gate arithmetic of
 // ptlflow/models/raft/update.py:58-73 and writes pixel-major f16/bf16 with 16-byte stores.
 #include "umma.cuh"
@@ -19,12 +22,13 @@ namespace pfb {
 using namespace sm100;
 
 constexpr int kATileBytes = 128 * 128;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 
 struct __align__(8) ConvBars {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t acc_full;
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
   uint32_t tmem_base;
 };
 
@@ -33,7 +37,11 @@ struct ConvUmmaArgs {
   int src_chunks[PFB_MAX_SRC];   // 64-channel chunks per source
   int src_coff[PFB_MAX_SRC];     // first channel inside the source tensor
   int B, H, W, KH, KW;
-  int NT;                        // N tile (multiple of 16, <= 256)
+  int NT;                        // N tile (multiple of 32, <= 256)
+  int n_tiles;                   // N tiles per M tile
+  int TW, TH, tw_shift;          // M tile = TW x TH pixels (TW * TH = 128, powers of two)
+  int tiles_x, tiles_y, n_work;  // work items = tiles_x * tiles_y * B * n_tiles
+  int acc_stride;                // TMEM column offset between the two accumulators
   int Cout, Cout_pad_k;
   int stages, stage_bytes;
   const float* bias;
@@ -91,8 +99,8 @@ __device__ __forceinline__ void load32(const T* src, float (&v)[32]) {
   }
 }
 
-template <typename T, int TMEM_COLS>
-__global__ void __launch_bounds__(192, 2)
+template <typename T>
+__global__ void __launch_bounds__(192, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW, const ConvUmmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -100,29 +108,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   ConvBars* bars = reinterpret_cast<ConvBars*>(smem + a.stages * a.stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int PW = (a.W + 15) >> 4, PH = (a.H + 7) >> 3;
-  int t = blockIdx.x;
-  const int pw = t % PW;
-  t /= PW;
-  const int ph = t % PH;
-  const int b = t / PH;
-  const int n0 = blockIdx.y * a.NT;
-  const int x0 = pw * 16, y0 = ph * 8;
-
   int chunks_per_tap = 0;
   for (int s = 0; s < a.nsrc; ++s) chunks_per_tap += a.src_chunks[s];
   const int taps = a.KH * a.KW;
   const int ksteps = taps * chunks_per_tap;
+  const int tiles_m = a.tiles_x * a.tiles_y * a.B;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
-    mbar_init(&bars->acc_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars->acc_full[t], 1);
+      mbar_init(&bars->acc_empty[t], 4);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == 5) tmem_alloc<512>(&bars->tmem_base);
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tm0);
     prefetch_tmap(&tmW);
@@ -132,24 +135,41 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  // work item w -> (n tile, image, tile row, tile col); n-tile major so concurrent CTAs share the weight tile in L2
+  auto decode = [&](int w, int& n0, int& b, int& y0, int& x0) {
+    const int nt = w / tiles_m;
+    int m = w - nt * tiles_m;
+    const int px = m % a.tiles_x;
+    m /= a.tiles_x;
+    const int py = m % a.tiles_y;
+    b = m / a.tiles_y;
+    n0 = nt * a.NT;
+    y0 = py * a.TH;
+    x0 = px * a.TW;
+  };
+
   if (warp == 4) {
     // ================= TMA producer =================
     if (lane == 0) {
       const int ph2 = a.KH >> 1, pw2 = a.KW >> 1;
       const uint32_t tx = kATileBytes + a.NT * 128;
       int it = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int dy = tap / a.KW - ph2, dx = tap % a.KW - pw2;
-        int kidx = 0;
-        for (int s = 0; s < a.nsrc; ++s) {
-          const CUtensorMap* tm = s == 0 ? &tm0 : (s == 1 ? &tm1 : &tm2);
-          for (int c = 0; c < a.src_chunks[s]; ++c, ++kidx, ++it) {
-            const int st = it % a.stages, use = it / a.stages;
-            uint8_t* sa = smem + st * a.stage_bytes;
-            mbar_wait(&bars->empty[st], (use & 1) ^ 1);
-            mbar_arrive_expect_tx(&bars->full[st], tx);
-            tma_load_4d(sa, tm, &bars->full[st], a.src_coff[s] + c * 64, x0 + dx, y0 + dy, b);
-            tma_load_2d(sa + kATileBytes, &tmW, &bars->full[st], kidx * 64, tap * a.Cout_pad_k + n0);
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+        int n0, b, y0, x0;
+        decode(w, n0, b, y0, x0);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = tap / a.KW - ph2, dx = tap % a.KW - pw2;
+          int kidx = 0;
+          for (int s = 0; s < a.nsrc; ++s) {
+            const CUtensorMap* tm = s == 0 ? &tm0 : (s == 1 ? &tm1 : &tm2);
+            for (int c = 0; c < a.src_chunks[s]; ++c, ++kidx, ++it) {
+              const int st = it % a.stages, use = it / a.stages;
+              uint8_t* sa = smem + st * a.stage_bytes;
+              mbar_wait(&bars->empty[st], (use & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars->full[st], tx);
+              tma_load_4d(sa, tm, &bars->full[st], a.src_coff[s] + c * 64, x0 + dx, y0 + dy, b);
+              tma_load_2d(sa + kATileBytes, &tmW, &bars->full[st], kidx * 64, tap * a.Cout_pad_k + n0);
+            }
           }
         }
       }
@@ -158,105 +178,121 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, a.NT, a.ab_fmt);
-      for (int it = 0; it < ksteps; ++it) {
-        const int st = it % a.stages, use = it / a.stages;
-        uint8_t* sa = smem + st * a.stage_bytes;
-        mbar_wait(&bars->full[st], use & 1);
+      int it = 0, i = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++i) {
+        const int t = i & 1, tuse = i >> 1;
+        mbar_wait(&bars->acc_empty[t], (tuse & 1) ^ 1);
         tc_fence_after();
-        const uint64_t da = make_desc_k_sw128(smem_u32(sa));
-        const uint64_t db = make_desc_k_sw128(smem_u32(sa + kATileBytes));
+        const uint32_t d = tmem_base + t * a.acc_stride;
+        for (int k = 0; k < ksteps; ++k, ++it) {
+          const int st = it % a.stages, use = it / a.stages;
+          uint8_t* sa = smem + st * a.stage_bytes;
+          mbar_wait(&bars->full[st], use & 1);
+          tc_fence_after();
+          const uint64_t da = make_desc_k_sw128(smem_u32(sa));
+          const uint64_t db = make_desc_k_sw128(smem_u32(sa + kATileBytes));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, (it | kk) != 0);
-        umma_commit(&bars->empty[st]);
+          for (int kk = 0; kk < 4; ++kk) umma_f16(d, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, (k | kk) != 0);
+          umma_commit(&bars->empty[st]);
+        }
+        umma_commit(&bars->acc_full[t]);
       }
-      umma_commit(&bars->acc_full);
     }
   } else {
     // ================= epilogue: thread <-> pixel, 32 output channels at a time =================
     const int row = warp * 32 + lane;
-    const int y = y0 + (row >> 4), x = x0 + (row & 15);
-    const bool ok = (y < a.H) && (x < a.W);
-    const size_t p = ((size_t)b * a.H + (ok ? y : 0)) * a.W + (ok ? x : 0);
-    mbar_wait(&bars->acc_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int hd = a.hidden;
-    for (int c = 0; c < a.NT; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(taddr + c, r);
-      tmem_ld_wait();
-      const int n = n0 + c;  // first output channel of this chunk
-      float v[32];
+    int i = 0;
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++i) {
+      int n0, b, y0, x0;
+      decode(w, n0, b, y0, x0);
+      const int t = i & 1, tuse = i >> 1;
+      const int y = y0 + (row >> a.tw_shift), x = x0 + (row & (a.TW - 1));
+      const bool ok = (y < a.H) && (x < a.W);
+      const size_t p = ((size_t)b * a.H + (ok ? y : 0)) * a.W + (ok ? x : 0);
+      mbar_wait(&bars->acc_full[t], tuse & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + t * a.acc_stride + ((uint32_t)(warp * 32) << 16);
+      for (int c = 0; c < a.NT; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        const int n = n0 + c;  // first output channel of this chunk
+        float v[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 bb = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bb.x;
-        v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
-        v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z;
-        v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
-      }
-      if (!ok) continue;
-      T* out = reinterpret_cast<T*>(a.out);
-      switch (a.epilogue) {
-        case PFB_EPI_LINEAR: {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] *= a.scale;
-          store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
-          break;
+        for (int q = 0; q < 8; ++q) {
+          float4 bb = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bb.x;
+          v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
+          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z;
+          v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
         }
-        case PFB_EPI_RELU: {
+        if (!ok) continue;
+        T* out = reinterpret_cast<T*>(a.out);
+        switch (a.epilogue) {
+          case PFB_EPI_LINEAR: {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
-          store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
-          break;
-        }
-        case PFB_EPI_RELU_APPEND_FLOW: {
+            for (int e = 0; e < 32; ++e) v[e] *= a.scale;
+            store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            break;
+          }
+          case PFB_EPI_RELU: {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
-          int valid = a.Cout - n;
-          if (valid > 0 && valid <= 30) {  // the chunk that holds the last real channel also takes the 2 flow columns
-            const float fx = a.flow[2 * p], fy = a.flow[2 * p + 1];
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+            store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            break;
+          }
+          case PFB_EPI_RELU_APPEND_FLOW: {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (e == valid) v[e] = fx;
-              if (e == valid + 1) v[e] = fy;
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+            int valid = a.Cout - n;
+            if (valid > 0 && valid <= 30) {  // the chunk that holds the last real channel also takes the 2 flow columns
+              const float fx = a.flow[2 * p], fy = a.flow[2 * p + 1];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                if (e == valid) v[e] = fx;
+                if (e == valid + 1) v[e] = fy;
+              }
+              valid += 2;
             }
-            valid += 2;
+            store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
+            break;
           }
-          store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
-          break;
-        }
-        case PFB_EPI_GRU_ZR: {
+          case PFB_EPI_GRU_ZR: {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
-          if (n < hd) {
-            store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
-          } else {
-            float h[32];
-            load32<T>(reinterpret_cast<const T*>(a.aux_h) + p * hd + (n - hd), h);
+            for (int e = 0; e < 32; ++e) v[e] = 1.f / (1.f + __expf(-v[e]));
+            if (n < hd) {
+              store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
+            } else {
+              float h[32];
+              load32<T>(reinterpret_cast<const T*>(a.aux_h) + p * hd + (n - hd), h);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] *= h[e];
-            store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
+              for (int e = 0; e < 32; ++e) v[e] *= h[e];
+              store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
+            }
+            break;
           }
-          break;
-        }
-        case PFB_EPI_GRU_Q: {
-          float h[32], z[32];
-          load32<T>(reinterpret_cast<const T*>(a.aux_h) + p * hd + n, h);
-          load32<T>(reinterpret_cast<const T*>(a.aux_z) + p * hd + n, z);
+          case PFB_EPI_GRU_Q: {
+            float h[32], z[32];
+            load32<T>(reinterpret_cast<const T*>(a.aux_h) + p * hd + n, h);
+            load32<T>(reinterpret_cast<const T*>(a.aux_z) + p * hd + n, z);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = (1.f - z[e]) * h[e] + z[e] * tanhf(v[e]);
-          store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
-          break;
+            for (int e = 0; e < 32; ++e) v[e] = (1.f - z[e]) * h[e] + z[e] * tanhf(v[e]);
+            store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
+            break;
+          }
+          default:
+            break;
         }
-        default:
-          break;
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[t]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 5) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,23 +333,32 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
 template <typename T>
 static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const ConvUmmaArgs& a, dim3 grid, size_t smem,
                             cudaStream_t s) {
-#define PFB_LAUNCH_COLS(COLS)                                                                                          \
-  do {                                                                                                                 \
-    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_umma_kernel<T, COLS><<<grid, 192, smem, s>>>(tms[0], tms[1], tms[2], tmW, a);                                 \
-  } while (0)
-  if (a.NT <= 32) PFB_LAUNCH_COLS(32);
-  else if (a.NT <= 64) PFB_LAUNCH_COLS(64);
-  else if (a.NT <= 128) PFB_LAUNCH_COLS(128);
-  else PFB_LAUNCH_COLS(256);
-#undef PFB_LAUNCH_COLS
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_umma_kernel<T><<<grid, 192, smem, s>>>(tms[0], tms[1], tms[2], tmW, a);
   PFB_LAUNCH_CHECK();
   return PFB_OK;
+}
+
+// M tile shape: TW x TH = 128 with the least padded area (ties -> the wider tile: fewer, longer TMA rows)
+static void pick_tile(int H, int W, int& TW, int& TH) {
+  long best = -1;
+  for (int tw = 128; tw >= 8; tw >>= 1) {
+    const int th = 128 / tw;
+    const long area = (long)ceil_div(W, tw) * tw * ceil_div(H, th) * th;
+    if (best < 0 || area < best) { best = area; TW = tw; TH = th; }
+  }
 }
 
 int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   ConvUmmaArgs a{};
   CUtensorMap tms[3];
+  pick_tile(p->H, p->W, a.TW, a.TH);
+  a.tw_shift = 0;
+  while ((1 << a.tw_shift) < a.TW) ++a.tw_shift;
   a.nsrc = p->nsrc;
   for (int i = 0; i < p->nsrc; ++i) {
     const pfb_conv_src& src = p->src[i];
@@ -322,13 +367,14 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
     // dim 0 ends at the source's last real channel: a partial last 64-chunk is zero-filled by the TMA unit
     uint64_t dims[4] = {(uint64_t)(src.offset + src.channels), (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)src.stride * 2, (uint64_t)p->W * src.stride * 2, (uint64_t)p->H * p->W * src.stride * 2};
-    uint32_t box[4] = {64, 16, 8, 1};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
     int rc = make_tensor_map(&tms[i], src.ptr, p->dtype, 4, dims, str, box);
     if (rc) return rc;
   }
   for (int i = p->nsrc; i < 3; ++i) tms[i] = tms[0];
-  const int n_tiles = ceil_div(p->Cout_pad_k, 256);
-  a.NT = p->Cout_pad_k / n_tiles;
+  a.n_tiles = ceil_div(p->Cout_pad_k, 256);
+  a.NT = p->Cout_pad_k / a.n_tiles;
+  a.acc_stride = a.NT > 128 ? 256 : 128;
   CUtensorMap tmW;
   {
     uint64_t dims[2] = {(uint64_t)p->Cin_pad, (uint64_t)p->KH * p->KW * p->Cout_pad_k};
@@ -338,17 +384,19 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
     if (rc) return rc;
   }
   a.B = p->B; a.H = p->H; a.W = p->W; a.KH = p->KH; a.KW = p->KW;
+  a.tiles_x = ceil_div(p->W, a.TW);
+  a.tiles_y = ceil_div(p->H, a.TH);
+  a.n_work = a.tiles_x * a.tiles_y * p->B * a.n_tiles;
   a.Cout = p->Cout; a.Cout_pad_k = p->Cout_pad_k;
   a.stage_bytes = kATileBytes + a.NT * 128;
-  a.stages = (100 * 1024) / a.stage_bytes;
+  a.stages = (212 * 1024) / a.stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
-  if (a.stages < 2) a.stages = 2;
   a.bias = p->bias; a.epilogue = p->epilogue; a.scale = p->scale;
   a.out = p->out; a.out_stride = p->out_stride; a.out_offset = p->out_offset;
   a.aux_h = p->aux_h; a.aux_z = p->aux_z; a.hidden = p->hidden; a.flow = p->flow;
   a.ab_fmt = p->dtype == PFB_F16 ? 0 : 1;
   const size_t smem = (size_t)a.stages * a.stage_bytes + sizeof(ConvBars) + 1024;
-  dim3 grid(ceil_div(p->W, 16) * ceil_div(p->H, 8) * p->B, n_tiles);
+  dim3 grid(a.n_work < sm_count() ? a.n_work : sm_count());
   ProfScope prof(KC_CONV, s);
   if (p->dtype == PFB_F16) return launch_conv_umma<__half>(tms, tmW, a, grid, smem, s);
   return launch_conv_umma<__nv_bfloat16>(tms, tmW, a, grid, smem, s);

@@ -148,6 +148,74 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(LevelTable lv, const f
     for (int c = planes + lane; c < out_stride; c += 32) out[(size_t)q * out_stride + c] = from_f32<TO>(0.f);
 }
 
+// Fast path (radius <= 4, levels <= 4, pixel-major output): every lane issues the gathers of ALL levels
+// before any is consumed (16 independent loads in flight per lane instead of 4 dependent rounds), the four
+// windows live side by side in shared memory, and the L*(2r+1)^2 outputs are written as one coalesced run.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(128) corr_lookup_r4_kernel(LevelTable lv, const float* __restrict__ coords,
+                                                             TO* __restrict__ out, int nq, int levels, int r,
+                                                             int out_stride) {
+  __shared__ float smem[4][4 * 100];
+  __shared__ float wts[4][4][4];
+  const int D = 2 * r + 2, K = 2 * r + 1, DD = D * D, KK = K * K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* win = smem[warp];
+  const int q = blockIdx.x * 4 + warp;
+  if (q >= nq) return;
+  const float cx = coords[2 * (size_t)q], cy = coords[2 * (size_t)q + 1];
+  float vals[4][4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    if (l < levels) {
+      const float s = 1.0f / (float)(1 << l);
+      const float x = cx * s, y = cy * s;
+      const int Hl = lv.h[l], Wl = lv.w[l];
+      const bool finite = (fabsf(x) < 1e7f) && (fabsf(y) < 1e7f);
+      const float xf = finite ? floorf(x) : -1e6f, yf = finite ? floorf(y) : -1e6f;
+      const float fx = finite ? x - xf : 0.f, fy = finite ? y - yf : 0.f;
+      if (lane == 0) {
+        wts[warp][l][0] = (1.f - fx) * (1.f - fy);
+        wts[warp][l][1] = fx * (1.f - fy);
+        wts[warp][l][2] = (1.f - fx) * fy;
+        wts[warp][l][3] = fx * fy;
+      }
+      const int x0 = (int)xf - r, y0 = (int)yf - r;
+      const T* base = reinterpret_cast<const T*>(lv.ptr[l]) + (size_t)q * Hl * Wl;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = lane + 32 * k;
+        const int j = t / D, i = t - j * D;
+        const int xi = x0 + i, yi = y0 + j;
+        float v = 0.f;
+        if (t < DD && xi >= 0 && xi < Wl && yi >= 0 && yi < Hl) v = to_f32(__ldg(base + (size_t)yi * Wl + xi));
+        vals[l][k] = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    if (l < levels) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = lane + 32 * k;
+        const int j = t / D, i = t - j * D;
+        if (t < DD) win[l * 100 + i * D + j] = vals[l][k];
+      }
+    }
+  }
+  __syncwarp();
+  const int planes = levels * KK;
+  TO* o = out + (size_t)q * out_stride;
+  for (int c = lane; c < planes; c += 32) {
+    const int l = c / KK, rem = c - l * KK;
+    const int i = rem / K, j = rem - i * K;
+    const float* w = win + l * 100;
+    const float* ww = wts[warp][l];
+    o[c] = from_f32<TO>(ww[0] * w[i * D + j] + ww[1] * w[(i + 1) * D + j] + ww[2] * w[i * D + j + 1] + ww[3] * w[(i + 1) * D + j + 1]);
+  }
+  for (int c = planes + lane; c < out_stride; c += 32) o[c] = from_f32<TO>(0.f);
+}
+
 // =====================================================================================
 // a4: on-the-fly lookup.  One warp per query; the query's feature vector sits in shared memory
 // as fp32; each lane owns integer taps of the window and runs the full C-long dot product with
@@ -344,6 +412,16 @@ static int launch_lookup_t(const LevelTable& lv, const float* coords, void* out,
   size_t smem = (size_t)warps * D * D * sizeof(float);
   dim3 grid(ceil_div(nq, warps));
   ProfScope prof(KC_LOOKUP, s);
+  if (!nchw && radius <= 4 && levels <= 4) {
+    if (out_dtype == PFB_F32)
+      corr_lookup_r4_kernel<T, float><<<grid, 128, 0, s>>>(lv, coords, (float*)out, nq, levels, radius, out_stride);
+    else if (out_dtype == PFB_F16)
+      corr_lookup_r4_kernel<T, __half><<<grid, 128, 0, s>>>(lv, coords, (__half*)out, nq, levels, radius, out_stride);
+    else
+      corr_lookup_r4_kernel<T, __nv_bfloat16><<<grid, 128, 0, s>>>(lv, coords, (__nv_bfloat16*)out, nq, levels, radius, out_stride);
+    PFB_LAUNCH_CHECK();
+    return PFB_OK;
+  }
   if (out_dtype == PFB_F32)
     corr_lookup_kernel<T, float><<<grid, warps * 32, smem, s>>>(lv, coords, (float*)out, nq, hw, levels, radius, nchw, out_stride);
   else if (out_dtype == PFB_F16)

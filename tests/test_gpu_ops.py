@@ -67,7 +67,7 @@ def test_volume_pyramid_lookup_vs_reference_vectors(dtype, tol):
     # pixel-major layout with zero-filled pad columns returns the same numbers
     planes = g["lookup"].shape[1]
     look2 = ops.corr_lookup(pyr, _nhwc(coords), recipe["radius"], (recipe["h"], recipe["w"]), nchw=False, out_dtype=torch.float32, out_stride=planes + 60)
-    assert torch.equal(look2[..., :planes].permute(0, 3, 1, 2), look)
+    assert (look2[..., :planes].permute(0, 3, 1, 2) - look).abs().max().item() < 1e-5  # fast path (r<=4) vs generic kernel
     assert look2[..., planes:].abs().max().item() == 0.0
 
 
