@@ -254,6 +254,23 @@ PFB_API int pfb_raft_update_iter(const pfb_raft_cfg* cfg, const pfb_raft_weights
                          const void* corr, void* mask_out, pfb_stream stream);
 
 /* ------------------------------------------------------------------------------------
+ * Encoder-side kernels (the callers either side of the path).
+ * The 3x3 / 7x7 / 1x1 convolutions of BasicEncoder / SmallEncoder (extractor.py:122-267) still run in
+ * cuDNN; pre-processing, instance norm + ReLU (+ residual) and the residual joins are fused here.
+ * ---------------------------------------------------------------------------------- */
+/* images [B,2,3,H,W] BGR in [0,1] (NCHW) -> out [2B,Hp,Wp,3] pixel-major RGB in [-1,1], replicate padded;
+ * the first B entries are frame 1, the next B frame 2.     raft.py:127-135, base_model.py:206-246 */
+PFB_API int pfb_preprocess_frames(const void* images, void* out, int B, int H, int W, int Hp, int Wp, int pad_top,
+                                  int pad_left, pfb_dtype dtype, pfb_stream stream);
+/* y = act(IN(x)) or, with residual, y = relu(residual + act(IN(x)));  x, y, residual: [B,H,W,C].
+ * IN = nn.InstanceNorm2d defaults (no affine, biased variance, eps).   extractor.py:29-31,52-58 */
+PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C);
+PFB_API int pfb_instance_norm_act(const void* x, void* y, const void* residual, void* workspace, int B, int H, int W, int C,
+                                  float eps, int relu, pfb_dtype dtype, pfb_stream stream);
+/* y = relu(residual + (relu_x ? relu(x) : x)) elementwise over n values */
+PFB_API int pfb_add_act(const void* x, const void* residual, void* y, size_t n, int relu_x, pfb_dtype dtype, pfb_stream stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): launch accounting and live per-kernel-class timing.
  * kernel_class: 0 volume, 1 pool, 2 lookup, 3 on-the-fly lookup, 4 conv, 5 upsample, 6 misc;
  * -1 = all.  pfb_profile_collect synchronises the device, writes summed milliseconds and span

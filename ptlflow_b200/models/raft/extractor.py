@@ -5,6 +5,9 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
 
 
 def _norm(kind: str, channels: int, groups: int = 8) -> nn.Module:
@@ -69,6 +72,26 @@ class BottleneckBlock(nn.Module):
         return self.relu(x + y)
 
 
+def _fold(conv: nn.Conv2d, norm: nn.Module, dtype, device):
+    """(weight, bias) of ``conv`` in channels_last storage; an eval-mode BatchNorm that follows is folded in
+    (y = s * conv(x) + t  ->  weight * s, bias * s + t).  Instance norm / identity leave the conv as is."""
+    w = conv.weight.detach().to(device=device, dtype=torch.float32)
+    b = conv.bias.detach().to(device=device, dtype=torch.float32) if conv.bias is not None else torch.zeros(w.shape[0], device=device)
+    if isinstance(norm, nn.BatchNorm2d):
+        s = norm.weight.detach().float().to(device) / torch.sqrt(norm.running_var.detach().float().to(device) + norm.eps)
+        t = norm.bias.detach().float().to(device) - norm.running_mean.detach().float().to(device) * s
+        w = w * s.view(-1, 1, 1, 1)
+        b = b * s + t
+    return w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype)
+
+
+def _conv_pm(x: torch.Tensor, wb, stride: int, padding: int) -> torch.Tensor:
+    """cuDNN convolution on a pixel-major tensor [N,H,W,C] -> [N,H',W',C'] (channels_last in and out, no copies)."""
+    y = F.conv2d(x.permute(0, 3, 1, 2), wb[0], wb[1], stride=stride, padding=padding)
+    y = y.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else y.contiguous()
+
+
 class _Encoder(nn.Module):
     block = ResidualBlock
     widths = (64, 64, 96, 128)
@@ -94,6 +117,60 @@ class _Encoder(nn.Module):
 
     def _stage(self, cin: int, cout: int, stride: int) -> nn.Sequential:
         return nn.Sequential(self.block(cin, cout, self.norm_fn, stride=stride), self.block(cout, cout, self.norm_fn, stride=1))
+
+    # ---- inference path: cuDNN convs + this library's fused norm / activation / residual kernels ----
+    def _signature(self, dtype, device):
+        return (dtype, str(device)) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
+            tuple((b.data_ptr(), b._version) for b in self.buffers())
+
+    def _prepared(self, dtype, device):
+        sig = self._signature(dtype, device)
+        cache = getattr(self, "_prep_cache", None)
+        if cache is not None and cache[0] == sig:
+            return cache[1]
+        prep = {"conv1": _fold(self.conv1, self.norm1, dtype, device), "conv2": _fold(self.conv2, nn.Identity(), dtype, device), "blocks": []}
+        for layer in (self.layer1, self.layer2, self.layer3):
+            for blk in layer:
+                e = {"stride": blk.conv2.stride[0] if isinstance(blk, BottleneckBlock) else blk.conv1.stride[0]}
+                names = ("conv1", "conv2", "conv3") if isinstance(blk, BottleneckBlock) else ("conv1", "conv2")
+                for i, nme in enumerate(names, start=1):
+                    e[nme] = _fold(getattr(blk, nme), getattr(blk, f"norm{i}"), dtype, device)
+                if blk.downsample is not None:
+                    e["down"] = _fold(blk.downsample[0], blk.downsample[1], dtype, device)
+                prep["blocks"].append(e)
+        self._prep_cache = (sig, prep)
+        return prep
+
+    def forward_pm(self, x: torch.Tensor) -> torch.Tensor:
+        """x: pixel-major frames [N,H,W,3] on CUDA -> features [N,H/8,W/8,C] (eval semantics of
+        extractor.py:171-194 / :246-267).  Batch norm is folded into the convolutions, instance norm + ReLU
+        (+ residual join) is one fused pass (pfb_instance_norm_act) instead of five PyTorch kernels."""
+        if self.norm_fn not in ("instance", "batch", "none"):
+            return ops.to_pixel_major(self.forward(x.permute(0, 3, 1, 2)))
+        inst = self.norm_fn == "instance"
+        prep = self._prepared(x.dtype, x.device)
+
+        def act(y, relu=True, residual=None):
+            if inst:
+                return ops.instance_norm_act(y, relu=relu, residual=residual, out=y if residual is None else None)
+            if residual is not None:
+                return ops.add_act(y, residual, relu_x=relu)
+            return torch.relu_(y) if relu else y
+
+        x = act(_conv_pm(x, prep["conv1"], 2, 3))
+        for e in prep["blocks"]:
+            s = e["stride"]
+            if "conv3" in e:  # bottleneck: 1x1 -> 3x3 (stride) -> 1x1
+                y = act(_conv_pm(x, e["conv1"], 1, 0))
+                y = act(_conv_pm(y, e["conv2"], s, 1))
+                y = _conv_pm(y, e["conv3"], 1, 0)
+            else:  # residual: 3x3 (stride) -> 3x3
+                y = act(_conv_pm(x, e["conv1"], s, 1))
+                y = _conv_pm(y, e["conv2"], 1, 1)
+            if "down" in e:
+                x = act(_conv_pm(x, e["down"], s, 0), relu=False)
+            x = act(y, relu=True, residual=x)
+        return _conv_pm(x, prep["conv2"], 1, 0)
 
     def forward(self, x):
         """Accepts one tensor or a list/tuple of two (processed as one batch: instance norm is

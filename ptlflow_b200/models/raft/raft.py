@@ -82,17 +82,17 @@ class RAFT(BaseModel):
             self._engine = eng
         return eng
 
-    def _encode(self, image1: torch.Tensor, image2: torch.Tensor):
-        x1 = image1.contiguous(memory_format=torch.channels_last)
-        x2 = image2.contiguous(memory_format=torch.channels_last)
-        if x1.dtype == torch.float32 and self.strict_fp32:
+    def _encode(self, frames: torch.Tensor, B: int):
+        """frames: pixel-major [2B,Hp,Wp,3] (frame 1 of every pair first).  Both frames go through fnet as one
+        batch (instance norm is per sample, extractor.py:173-176); cnet sees frame 1 only."""
+        if frames.dtype == torch.float32 and self.strict_fp32:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                fmap1, fmap2 = self.fnet([x1, x2])
-                cnet = self.cnet(x1)
+                fmaps = self.fnet.forward_pm(frames)
+                cnet = self.cnet.forward_pm(frames[:B])
         else:
-            fmap1, fmap2 = self.fnet([x1, x2])
-            cnet = self.cnet(x1)
-        return ops.to_pixel_major(fmap1), ops.to_pixel_major(fmap2), ops.to_pixel_major(cnet)
+            fmaps = self.fnet.forward_pm(frames)
+            cnet = self.cnet.forward_pm(frames[:B])
+        return fmaps[:B], fmaps[B:], cnet
 
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Estimate optical flow between a pair of frames (eval semantics of raft.py:125-194)."""
@@ -102,10 +102,15 @@ class RAFT(BaseModel):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.update_block.parameters()) and self.training:
             raise NotImplementedError("ptlflow_b200 implements the inference hot path; call under torch.no_grad() / model.eval()")
         with torch.no_grad():
-            images, resizer = self.preprocess_images(images, bgr_add=-0.5, bgr_mult=2.0, bgr_to_rgb=True, resize_mode="pad",
-                                                     pad_mode="replicate", pad_two_side=True)
+            # fused equivalent of preprocess_images(bgr_add=-0.5, bgr_mult=2, bgr_to_rgb=True, pad "replicate" two-sided)
+            # (raft.py:127-135): one kernel, output already pixel-major; the caller's tensor is only read
+            from ...utils.utils import InputPadder
+
+            images = images.contiguous()
+            resizer = InputPadder(images.shape, stride=self.output_stride, pad_mode="replicate", two_side_pad=True)
             B = images.shape[0]
-            fmap1, fmap2, cnet = self._encode(images[:, 0], images[:, 1])
+            frames = ops.preprocess_frames(images, resizer.tgt_size, resizer.pad_top_left)
+            fmap1, fmap2, cnet = self._encode(frames, B)
             _, H8, W8, _ = fmap1.shape
             eng = self._get_engine(fmap1.dtype, fmap1.device)
             net, inp = ops.context_split(cnet, self.hidden_dim, self.context_dim)

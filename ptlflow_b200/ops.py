@@ -238,3 +238,55 @@ def context_split(cnet: torch.Tensor, hidden: int, context: int):
         check(load().pfb_context_split(cnet.data_ptr(), net.data_ptr(), inp.data_ptr(), B, H, W, hidden, context,
                                        dtype_code(cnet.dtype), stream_ptr(cnet.device)), "context_split")
     return net, inp
+
+
+# ------------------------------------------------------------------------------------------
+# encoder-side kernels
+# ------------------------------------------------------------------------------------------
+def preprocess_frames(images: torch.Tensor, padded_hw, pad_top_left) -> torch.Tensor:
+    """images [B,2,3,H,W] (BGR, [0,1]) -> [2B,Hp,Wp,3] pixel-major RGB in [-1,1], replicate padded; frame-major."""
+    require_cuda(images, "images")
+    B, two, three, H, W = images.shape
+    if two != 2 or three != 3:
+        raise RuntimeError("preprocess_frames: expected images of shape [B,2,3,H,W]")
+    Hp, Wp = padded_hw
+    out = torch.empty((2 * B, Hp, Wp, 3), dtype=images.dtype, device=images.device)
+    with torch.cuda.device(images.device):
+        check(load().pfb_preprocess_frames(images.data_ptr(), out.data_ptr(), B, H, W, Hp, Wp, pad_top_left[0], pad_top_left[1],
+                                           dtype_code(images.dtype), stream_ptr(images.device)), "preprocess_frames")
+    return out
+
+
+_inorm_ws = {}
+
+
+def instance_norm_act(x: torch.Tensor, relu: bool = True, residual: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B,H,W,C] -> act(IN(x)), or relu(residual + act(IN(x)))."""
+    require_cuda(x, "x")
+    B, H, W, Cc = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    key = (str(x.device), B * Cc)
+    ws = _inorm_ws.get(key)
+    if ws is None:
+        ws = torch.empty(B * Cc * 2, dtype=torch.float64, device=x.device)
+        _inorm_ws[key] = ws
+    if residual is not None:
+        require_cuda(residual, "residual")
+        assert residual.shape == x.shape
+    with torch.cuda.device(x.device):
+        check(load().pfb_instance_norm_act(x.data_ptr(), y.data_ptr(), residual.data_ptr() if residual is not None else None,
+                                           ws.data_ptr(), B, H, W, Cc, eps, int(relu), dtype_code(x.dtype), stream_ptr(x.device)),
+              "instance_norm_act")
+    return y
+
+
+def add_act(x: torch.Tensor, residual: torch.Tensor, relu_x: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """relu(residual + relu(x)) (relu_x) or relu(residual + x)."""
+    require_cuda(x, "x"); require_cuda(residual, "residual")
+    assert x.shape == residual.shape and x.dtype == residual.dtype
+    y = out if out is not None else torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(load().pfb_add_act(x.data_ptr(), residual.data_ptr(), y.data_ptr(), x.numel(), int(relu_x), dtype_code(x.dtype),
+                                 stream_ptr(x.device)), "add_act")
+    return y

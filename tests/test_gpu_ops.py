@@ -265,3 +265,61 @@ def test_full_size_properties(dtype):
     a = ops.corr_lookup(pyr, noisy, r, (h, w), out_dtype=torch.float32)
     bb = ops.corr_lookup_onthefly(f1, fpyr, noisy, r, out_dtype=torch.float32)
     assert (a - bb).abs().max().item() < (2e-4 if dtype == torch.float32 else 5e-2)
+
+
+# ------------------------------------------------------------------------------------------
+# encoder-side kernels (first step)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w", [(37, 50), (128, 160), (436, 1024)])
+def test_preprocess_frames_vs_oracle(h, w):
+    from ptlflow_b200.utils.utils import InputPadder
+
+    ops = _ops()
+    img = torch.from_numpy(synth.synth_images(2, h, w, 3, "noise"))
+    ref, pads = O.preprocess(img)  # [B,2,3,Hp,Wp]
+    padder = InputPadder(img.shape, stride=8)
+    out = ops.preprocess_frames(img.to(DEV), padder.tgt_size, padder.pad_top_left)
+    assert out.shape == (4, ref.shape[-2], ref.shape[-1], 3)
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert torch.equal(got[:2], ref[:, 0]) and torch.equal(got[2:], ref[:, 1])
+
+
+@pytest.mark.parametrize("c", [64, 96, 128, 24, 8])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 4e-3)])
+def test_instance_norm_act_vs_torch(c, dtype, tol):
+    ops = _ops()
+    b, h, w = 3, 19, 27
+    x = torch.from_numpy(synth.synth_normal("in/x", (b, c, h, w), 1, scale=2.0)) + 0.7
+    res = torch.relu(torch.from_numpy(synth.synth_normal("in/r", (b, c, h, w), 2)))
+    xq, rq = x.to(dtype).float(), res.to(dtype).float()
+    base = F.instance_norm(xq, eps=1e-5)
+    xd, rd = _nhwc(x, dtype), _nhwc(res, dtype)
+    y = ops.instance_norm_act(xd, relu=True)
+    assert (y.permute(0, 3, 1, 2).float().cpu() - torch.relu(base)).abs().max().item() < tol
+    y = ops.instance_norm_act(xd, relu=False)
+    assert (y.permute(0, 3, 1, 2).float().cpu() - base).abs().max().item() < tol
+    y = ops.instance_norm_act(xd, relu=True, residual=rd)
+    assert (y.permute(0, 3, 1, 2).float().cpu() - torch.relu(rq + torch.relu(base))).abs().max().item() < 2 * tol
+    y = ops.add_act(xd, rd, relu_x=True)
+    assert (y.permute(0, 3, 1, 2).float().cpu() - torch.relu(rq + torch.relu(xq))).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("variant", ["raft", "raft_small"])
+def test_encoders_vs_oracle_fp32(variant):
+    import ptlflow_b200 as pb
+
+    small = variant == "raft_small"
+    sd = synth.synth_state_dict(O.state_dict_shapes(variant), 3)
+    model = pb.get_model(variant)
+    model.load_state_dict(sd)
+    model = model.eval().to(DEV)
+    img = torch.from_numpy(synth.synth_images(2, 72, 104, 4, "smooth"))
+    x, _ = O.preprocess(img)
+    frames = x.transpose(0, 1).reshape(4, 3, 72, 104)  # frame-major
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        f = model.fnet.forward_pm(frames.permute(0, 2, 3, 1).contiguous().to(DEV))
+        c = model.cnet.forward_pm(frames[:2].permute(0, 2, 3, 1).contiguous().to(DEV))
+    fref = O.encoder(frames, sd, "fnet.", "instance", small)
+    cref = O.encoder(frames[:2], sd, "cnet.", "none" if small else "batch", small)
+    assert (f.permute(0, 3, 1, 2).cpu() - fref).abs().max().item() < 2e-4
+    assert (c.permute(0, 3, 1, 2).cpu() - cref).abs().max().item() < 2e-4
