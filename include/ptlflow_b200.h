@@ -267,8 +267,10 @@ PFB_API int pfb_preprocess_frames(const void* images, void* out, int B, int H, i
 PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C);
 PFB_API int pfb_instance_norm_act(const void* x, void* y, const void* residual, void* workspace, int B, int H, int W, int C,
                                   float eps, int relu, pfb_dtype dtype, pfb_stream stream);
-/* y = relu(residual + (relu_x ? relu(x) : x)) elementwise over n values */
-PFB_API int pfb_add_act(const void* x, const void* residual, void* y, size_t n, int relu_x, pfb_dtype dtype, pfb_stream stream);
+/* y = act(x + bias[c]) or, with residual, y = relu(residual + act(x + bias[c]));  bias fp32 [C] (may be NULL);
+ * workspace >= 8*C bytes.  Used for the batch-norm-folded context encoder (conv bias + BN shift) and conv2. */
+PFB_API int pfb_bias_act(const void* x, const float* bias, const void* residual, void* y, void* workspace, int B, int H, int W,
+                         int C, int relu, pfb_dtype dtype, pfb_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): launch accounting and live per-kernel-class timing.

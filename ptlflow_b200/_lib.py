@@ -101,7 +101,7 @@ SIGNATURES = {
     "pfb_preprocess_frames": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_instance_norm_workspace_bytes": (C.c_size_t, [_I, _I]),
     "pfb_instance_norm_act": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, C.c_float, _I, _I, _S]),
-    "pfb_add_act": (_I, [_P, _P, _P, C.c_size_t, _I, _I, _S]),
+    "pfb_bias_act": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_launch_count": (C.c_ulonglong, [_I]),
     "pfb_profile_enable": (_I, [_I]),
     "pfb_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), _I]),

@@ -73,40 +73,74 @@ __global__ void __launch_bounds__(256) inorm_stats_kernel(const T* __restrict__ 
   }
 }
 
-// y = act(norm(x)) ; with residual: y = relu(residual + act(norm(x)))
+// per-(sample, channel) scale / shift from the accumulated sums: y = x * rstd - mean * rstd
+__global__ void inorm_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ ss, int n, int HW, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = stats[2 * i] / HW;
+  double var = stats[2 * i + 1] / HW - mean * mean;
+  var = var < 0 ? 0 : var;
+  const float rstd = rsqrtf((float)var + eps);
+  ss[i] = make_float2(rstd, (float)(-mean) * rstd);
+}
+
+// y = act(x * scale + shift)  [+ residual -> relu];  scale/shift per (sample, channel) (ss_bstride = C) or per
+// channel (ss_bstride = 0).  8 channels (16 bytes) per thread.
 template <typename T>
-__global__ void inorm_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats, const T* __restrict__ residual,
-                                   T* __restrict__ y, int B, int HW, int C, float eps, int relu) {
-  const size_t total = (size_t)B * HW * C / 2;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const size_t e = idx * 2;
-    const int c = (int)(e % C);
-    const int b = (int)(e / ((size_t)HW * C));
-    const double* st = stats + ((size_t)b * C + c) * 2;
-    float o[2];
+__global__ void affine_act_kernel(const T* __restrict__ x, const float2* __restrict__ ss, const T* __restrict__ residual,
+                                  T* __restrict__ y, size_t total8, int HW, int C, int ss_bstride, int relu) {
+  const int c8n = C / 8;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total8; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % c8n) * 8;
+    const size_t b = idx / ((size_t)HW * c8n);
+    const float2* s = ss + b * ss_bstride + c0;
+    uint4 xv = reinterpret_cast<const uint4*>(x)[idx];
+    uint4 rv = residual ? reinterpret_cast<const uint4*>(residual)[idx] : make_uint4(0u, 0u, 0u, 0u);
+    const T* xe = reinterpret_cast<const T*>(&xv);
+    const T* re = reinterpret_cast<const T*>(&rv);
+    uint4 ov;
+    T* oe = reinterpret_cast<T*>(&ov);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const double mean = st[2 * k] / HW;
-      double var = st[2 * k + 1] / HW - mean * mean;
-      var = var < 0 ? 0 : var;
-      const float rstd = rsqrtf((float)var + eps);
-      float v = (to_f32(x[e + k]) - (float)mean) * rstd;
+    for (int k = 0; k < 8; ++k) {
+      const float2 sc = __ldg(s + k);
+      float v = fmaf(to_f32(xe[k]), sc.x, sc.y);
       if (relu) v = fmaxf(v, 0.f);
-      if (residual) v = fmaxf(to_f32(residual[e + k]) + v, 0.f);
-      o[k] = v;
+      if (residual) v = fmaxf(to_f32(re[k]) + v, 0.f);
+      oe[k] = from_f32<T>(v);
     }
-    y[e] = from_f32<T>(o[0]);
-    y[e + 1] = from_f32<T>(o[1]);
+    reinterpret_cast<uint4*>(y)[idx] = ov;
+  }
+}
+template <>
+__global__ void affine_act_kernel<float>(const float* __restrict__ x, const float2* __restrict__ ss,
+                                         const float* __restrict__ residual, float* __restrict__ y, size_t total8, int HW, int C,
+                                         int ss_bstride, int relu) {
+  const int c8n = C / 8;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total8; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % c8n) * 8;
+    const size_t b = idx / ((size_t)HW * c8n);
+    const float2* s = ss + b * ss_bstride + c0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 xv = reinterpret_cast<const float4*>(x)[2 * idx + h];
+      float4 rv = residual ? reinterpret_cast<const float4*>(residual)[2 * idx + h] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float xe[4] = {xv.x, xv.y, xv.z, xv.w}, re[4] = {rv.x, rv.y, rv.z, rv.w}, oe[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 sc = __ldg(s + 4 * h + k);
+        float v = fmaf(xe[k], sc.x, sc.y);
+        if (relu) v = fmaxf(v, 0.f);
+        if (residual) v = fmaxf(re[k] + v, 0.f);
+        oe[k] = v;
+      }
+      reinterpret_cast<float4*>(y)[2 * idx + h] = make_float4(oe[0], oe[1], oe[2], oe[3]);
+    }
   }
 }
 
-template <typename T>
-__global__ void add_act_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y, size_t n, int relu_x) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float v = to_f32(x[i]);
-    if (relu_x) v = fmaxf(v, 0.f);
-    y[i] = from_f32<T>(fmaxf(to_f32(residual[i]) + v, 0.f));
-  }
+__global__ void bias_to_ss_kernel(const float* __restrict__ bias, float2* __restrict__ ss, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) ss[i] = make_float2(1.f, bias ? bias[i] : 0.f);
 }
 
 }  // namespace pfb
@@ -130,41 +164,55 @@ extern "C" PFB_API int pfb_preprocess_frames(const void* images, void* out, int 
   return PFB_OK;
 }
 
-extern "C" PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C) { return (size_t)B * C * 2 * sizeof(double); }
+extern "C" PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C) {
+  return (size_t)B * C * (2 * sizeof(double) + sizeof(float2));
+}
+
+template <typename T>
+static int launch_affine(const void* x, const float2* ss, const void* residual, void* y, int B, int HW, int C, int bstride, int relu,
+                         cudaStream_t s) {
+  const size_t total8 = (size_t)B * HW * C / 8;
+  unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total8, 256), (size_t)sm_count() * 16);
+  affine_act_kernel<T><<<blocks, 256, 0, s>>>((const T*)x, ss, (const T*)residual, (T*)y, total8, HW, C, bstride, relu);
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}
 
 extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void* residual, void* workspace, int B, int H, int W,
                                              int C, float eps, int relu, pfb_dtype dtype, pfb_stream stream) {
   PFB_CHECK_ARG(x && y && workspace, "instance_norm_act: null pointer");
-  PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && C > 0 && C % 2 == 0 && C <= 512, "instance_norm_act: bad shape (C=%d must be even, <= 512)", C);
+  PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 512,
+                "instance_norm_act: bad shape (C=%d must be a multiple of 8, <= 512)", C);
   cudaStream_t s = as_stream(stream);
   const int HW = H * W;
   double* stats = reinterpret_cast<double*>(workspace);
-  PFB_CUDA(cudaMemsetAsync(stats, 0, pfb_instance_norm_workspace_bytes(B, C), s));
+  float2* ss = reinterpret_cast<float2*>(stats + (size_t)B * C * 2);
+  PFB_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(double), s));
   const int threads = 256;
-  PFB_CHECK_ARG(threads % (C / 2) == 0 || (C / 2) <= threads, "instance_norm_act: unsupported C=%d", C);
   int slabs = ceil_div(4 * sm_count(), B);
   if (slabs > ceil_div(HW, 64)) slabs = ceil_div(HW, 64);
   if (slabs < 1) slabs = 1;
   const int ppb = ceil_div(HW, slabs);
   dim3 grid(ceil_div(HW, ppb), B);
-  const size_t total2 = (size_t)B * HW * C / 2;
-  unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total2, 256), (size_t)sm_count() * 16);
   ProfScope prof(KC_MISC, s);
-  PFB_DISPATCH_DTYPE(dtype, T, {
-    inorm_stats_kernel<T><<<grid, threads, 4 * threads * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb);
-    inorm_apply_kernel<T><<<blocks, 256, 0, s>>>((const T*)x, stats, (const T*)residual, (T*)y, B, HW, C, eps, relu);
-  });
+  PFB_DISPATCH_DTYPE(dtype, T, { inorm_stats_kernel<T><<<grid, threads, 4 * threads * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb); });
   PFB_LAUNCH_CHECK();
+  inorm_finalize_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(stats, ss, B * C, HW, eps);
+  PFB_LAUNCH_CHECK();
+  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, ss, residual, y, B, HW, C, C, relu, s); });
   return PFB_OK;
 }
 
-extern "C" PFB_API int pfb_add_act(const void* x, const void* residual, void* y, size_t n, int relu_x, pfb_dtype dtype,
-                                   pfb_stream stream) {
-  PFB_CHECK_ARG(x && residual && y && n > 0 && dtype_ok(dtype), "add_act: bad arguments");
+// y = act(x + bias[c]) [+ residual -> relu]; bias fp32 [C] or NULL; workspace >= C * 8 bytes
+extern "C" PFB_API int pfb_bias_act(const void* x, const float* bias, const void* residual, void* y, void* workspace, int B, int H,
+                                    int W, int C, int relu, pfb_dtype dtype, pfb_stream stream) {
+  PFB_CHECK_ARG(x && y && workspace, "bias_act: null pointer");
+  PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bias_act: bad shape (C=%d must be a multiple of 8)", C);
   cudaStream_t s = as_stream(stream);
-  unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(n, 256), (size_t)sm_count() * 16);
+  float2* ss = reinterpret_cast<float2*>(workspace);
   ProfScope prof(KC_MISC, s);
-  PFB_DISPATCH_DTYPE(dtype, T, { add_act_kernel<T><<<blocks, 256, 0, s>>>((const T*)x, (const T*)residual, (T*)y, n, relu_x); });
+  bias_to_ss_kernel<<<ceil_div(C, 256), 256, 0, s>>>(bias, ss, C);
   PFB_LAUNCH_CHECK();
+  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, ss, residual, y, B, H * W, C, 0, relu, s); });
   return PFB_OK;
 }

@@ -82,12 +82,14 @@ def _fold(conv: nn.Conv2d, norm: nn.Module, dtype, device):
         t = norm.bias.detach().float().to(device) - norm.running_mean.detach().float().to(device) * s
         w = w * s.view(-1, 1, 1, 1)
         b = b * s + t
-    return w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype)
+    return w.to(dtype).contiguous(memory_format=torch.channels_last), b.contiguous()  # bias stays fp32: added by our kernels
 
 
 def _conv_pm(x: torch.Tensor, wb, stride: int, padding: int) -> torch.Tensor:
     """cuDNN convolution on a pixel-major tensor [N,H,W,C] -> [N,H',W',C'] (channels_last in and out, no copies)."""
-    y = F.conv2d(x.permute(0, 3, 1, 2), wb[0], wb[1], stride=stride, padding=padding)
+    # no bias here: PyTorch would add it as a separate broadcast kernel; it is folded into pfb_bias_act (batch / no norm)
+    # and is mathematically irrelevant in front of an instance norm (a per-channel constant is removed by the mean)
+    y = F.conv2d(x.permute(0, 3, 1, 2), wb[0], None, stride=stride, padding=padding)
     y = y.permute(0, 2, 3, 1)
     return y if y.is_contiguous() else y.contiguous()
 
@@ -150,27 +152,25 @@ class _Encoder(nn.Module):
         inst = self.norm_fn == "instance"
         prep = self._prepared(x.dtype, x.device)
 
-        def act(y, relu=True, residual=None):
+        def conv_act(x, wb, stride, padding, relu=True, residual=None):
+            y = _conv_pm(x, wb, stride, padding)
             if inst:
-                return ops.instance_norm_act(y, relu=relu, residual=residual, out=y if residual is None else None)
-            if residual is not None:
-                return ops.add_act(y, residual, relu_x=relu)
-            return torch.relu_(y) if relu else y
+                return ops.instance_norm_act(y, relu=relu, residual=residual, out=y)
+            return ops.bias_act(y, wb[1], relu=relu, residual=residual, out=y)
 
-        x = act(_conv_pm(x, prep["conv1"], 2, 3))
+        x = conv_act(x, prep["conv1"], 2, 3)
         for e in prep["blocks"]:
             s = e["stride"]
+            xs = conv_act(x, e["down"], s, 0, relu=False) if "down" in e else x
             if "conv3" in e:  # bottleneck: 1x1 -> 3x3 (stride) -> 1x1
-                y = act(_conv_pm(x, e["conv1"], 1, 0))
-                y = act(_conv_pm(y, e["conv2"], s, 1))
-                y = _conv_pm(y, e["conv3"], 1, 0)
+                y = conv_act(x, e["conv1"], 1, 0)
+                y = conv_act(y, e["conv2"], s, 1)
+                x = conv_act(y, e["conv3"], 1, 0, relu=True, residual=xs)
             else:  # residual: 3x3 (stride) -> 3x3
-                y = act(_conv_pm(x, e["conv1"], s, 1))
-                y = _conv_pm(y, e["conv2"], 1, 1)
-            if "down" in e:
-                x = act(_conv_pm(x, e["down"], s, 0), relu=False)
-            x = act(y, relu=True, residual=x)
-        return _conv_pm(x, prep["conv2"], 1, 0)
+                y = conv_act(x, e["conv1"], s, 1)
+                x = conv_act(y, e["conv2"], 1, 1, relu=True, residual=xs)
+        y = _conv_pm(x, prep["conv2"], 1, 0)
+        return ops.bias_act(y, prep["conv2"][1], relu=False, out=y)
 
     def forward(self, x):
         """Accepts one tensor or a list/tuple of two (processed as one batch: instance norm is

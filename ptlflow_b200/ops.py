@@ -269,7 +269,7 @@ def instance_norm_act(x: torch.Tensor, relu: bool = True, residual: Optional[tor
     key = (str(x.device), B * Cc)
     ws = _inorm_ws.get(key)
     if ws is None:
-        ws = torch.empty(B * Cc * 2, dtype=torch.float64, device=x.device)
+        ws = torch.empty(B * Cc * 3, dtype=torch.float64, device=x.device)  # sums (2 doubles) + scale/shift (2 floats)
         _inorm_ws[key] = ws
     if residual is not None:
         require_cuda(residual, "residual")
@@ -281,12 +281,21 @@ def instance_norm_act(x: torch.Tensor, relu: bool = True, residual: Optional[tor
     return y
 
 
-def add_act(x: torch.Tensor, residual: torch.Tensor, relu_x: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """relu(residual + relu(x)) (relu_x) or relu(residual + x)."""
-    require_cuda(x, "x"); require_cuda(residual, "residual")
-    assert x.shape == residual.shape and x.dtype == residual.dtype
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True, residual: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B,H,W,C] -> act(x + bias[c]), or relu(residual + act(x + bias[c])).  bias: fp32 [C] or None."""
+    require_cuda(x, "x")
+    B, H, W, Cc = x.shape
     y = out if out is not None else torch.empty_like(x)
+    key = (str(x.device), "bias", Cc)
+    ws = _inorm_ws.get(key)
+    if ws is None:
+        ws = torch.empty(Cc, dtype=torch.float64, device=x.device)
+        _inorm_ws[key] = ws
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == Cc and bias.is_cuda
     with torch.cuda.device(x.device):
-        check(load().pfb_add_act(x.data_ptr(), residual.data_ptr(), y.data_ptr(), x.numel(), int(relu_x), dtype_code(x.dtype),
-                                 stream_ptr(x.device)), "add_act")
+        check(load().pfb_bias_act(x.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                  residual.data_ptr() if residual is not None else None, y.data_ptr(), ws.data_ptr(), B, H, W, Cc,
+                                  int(relu), dtype_code(x.dtype), stream_ptr(x.device)), "bias_act")
     return y

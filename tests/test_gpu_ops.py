@@ -300,8 +300,11 @@ def test_instance_norm_act_vs_torch(c, dtype, tol):
     assert (y.permute(0, 3, 1, 2).float().cpu() - base).abs().max().item() < tol
     y = ops.instance_norm_act(xd, relu=True, residual=rd)
     assert (y.permute(0, 3, 1, 2).float().cpu() - torch.relu(rq + torch.relu(base))).abs().max().item() < 2 * tol
-    y = ops.add_act(xd, rd, relu_x=True)
-    assert (y.permute(0, 3, 1, 2).float().cpu() - torch.relu(rq + torch.relu(xq))).abs().max().item() < tol
+    bias = torch.from_numpy(synth.synth_normal("in/b", (c,), 3, scale=0.3))
+    y = ops.bias_act(xd, bias.to(DEV), relu=True, residual=rd)
+    assert (y.permute(0, 3, 1, 2).float().cpu() - torch.relu(rq + torch.relu(xq + bias.view(1, -1, 1, 1)))).abs().max().item() < 2 * tol
+    y = ops.bias_act(xd, bias.to(DEV), relu=False)
+    assert (y.permute(0, 3, 1, 2).float().cpu() - (xq + bias.view(1, -1, 1, 1))).abs().max().item() < 2 * tol
 
 
 @pytest.mark.parametrize("variant", ["raft", "raft_small"])
