@@ -78,32 +78,26 @@ __global__ void __launch_bounds__(256) conv_cout2_flow_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kFTH = 8, kFTW = 16;  // pixel tile of the 7x7 flow conv
-
-template <typename T>
-__global__ void __launch_bounds__(128) conv_flow7x7_kernel(const float* __restrict__ flow, int B, int H, int W,
+// pixel tile FTH x FTW (FTW a multiple of 16); <1,128> gives 440 blocks for the 55x128 grid (one wave at 3 blocks/SM)
+template <typename T, int FTH, int FTW>
+__global__ void __launch_bounds__(128, 3) conv_flow7x7_kernel(const float* __restrict__ flow, int B, int H, int W,
                                                            const T* __restrict__ w /*[49][2][Cout_pad]*/, int Cout,
                                                            int Cout_pad, const float* __restrict__ bias,
                                                            T* __restrict__ out, int out_stride, int out_offset) {
-  __shared__ float patch[kFTH + 6][kFTW + 6][2];
-  const int PW = (W + kFTW - 1) / kFTW, PH = (H + kFTH - 1) / kFTH;
+  __shared__ float2 patch[FTH + 6][FTW + 6];
+  const int PW = (W + FTW - 1) / FTW, PH = (H + FTH - 1) / FTH;
   int t = blockIdx.x;
   const int pw = t % PW;
   t /= PW;
   const int ph = t % PH;
   const int b = t / PH;
-  const int x0 = pw * kFTW, y0 = ph * kFTH;
-  for (int i = threadIdx.x; i < (kFTH + 6) * (kFTW + 6); i += blockDim.x) {
-    const int r = i / (kFTW + 6), c = i - r * (kFTW + 6);
+  const int x0 = pw * FTW, y0 = ph * FTH;
+  for (int i = threadIdx.x; i < (FTH + 6) * (FTW + 6); i += blockDim.x) {
+    const int r = i / (FTW + 6), c = i - r * (FTW + 6);
     const int y = y0 + r - 3, x = x0 + c - 3;
-    float fx = 0.f, fy = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) {
-      const float2 f = *reinterpret_cast<const float2*>(flow + 2 * ((size_t)(b * H + y) * W + x));
-      fx = f.x;
-      fy = f.y;
-    }
-    patch[r][c][0] = fx;
-    patch[r][c][1] = fy;
+    float2 f = make_float2(0.f, 0.f);
+    if (y >= 0 && y < H && x >= 0 && x < W) f = *reinterpret_cast<const float2*>(flow + 2 * ((size_t)(b * H + y) * W + x));
+    patch[r][c] = f;
   }
   __syncthreads();
   const int n = blockIdx.y * blockDim.x + threadIdx.x;
@@ -115,28 +109,32 @@ __global__ void __launch_bounds__(128) conv_flow7x7_kernel(const float* __restri
     wr[k][1] = to_f32(w[(size_t)(k * 2 + 1) * Cout_pad + n]);
   }
   const float bn = bias ? bias[n] : 0.f;
-  for (int ry = 0; ry < kFTH; ++ry) {
+  for (int ry = 0; ry < FTH; ++ry) {
     const int y = y0 + ry;
     if (y >= H) break;
-    float acc[kFTW];
+#pragma unroll 1
+    for (int seg = 0; seg < FTW; seg += 16) {
+      if (x0 + seg >= W) break;
+      float acc[16];
 #pragma unroll
-    for (int i = 0; i < kFTW; ++i) acc[i] = bn;
+      for (int i = 0; i < 16; ++i) acc[i] = bn;
 #pragma unroll
-    for (int ky = 0; ky < 7; ++ky) {
+      for (int ky = 0; ky < 7; ++ky) {
 #pragma unroll
-      for (int ix = 0; ix < kFTW + 6; ++ix) {
-        const float vx = patch[ry + ky][ix][0], vy = patch[ry + ky][ix][1];
+        for (int ix = 0; ix < 16 + 6; ++ix) {
+          const float2 v = patch[ry + ky][seg + ix];
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-          const int ox = ix - kx;
-          if (ox >= 0 && ox < kFTW) acc[ox] = fmaf(wr[ky * 7 + kx][1], vy, fmaf(wr[ky * 7 + kx][0], vx, acc[ox]));
+          for (int kx = 0; kx < 7; ++kx) {
+            const int ox = ix - kx;
+            if (ox >= 0 && ox < 16) acc[ox] = fmaf(wr[ky * 7 + kx][1], v.y, fmaf(wr[ky * 7 + kx][0], v.x, acc[ox]));
+          }
         }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < kFTW; ++i) {
-      const int x = x0 + i;
-      if (x < W) out[((size_t)(b * H + y) * W + x) * out_stride + out_offset + n] = from_f32<T>(fmaxf(acc[i], 0.f));
+      for (int i = 0; i < 16; ++i) {
+        const int x = x0 + seg + i;
+        if (x < W) out[((size_t)(b * H + y) * W + x) * out_stride + out_offset + n] = from_f32<T>(fmaxf(acc[i], 0.f));
+      }
     }
   }
 }
@@ -201,16 +199,21 @@ bool conv_flow7x7_supported(const pfb_conv_params* p) {
          p->src[0].offset == 0 && p->KH == 7 && p->KW == 7 && p->epilogue == PFB_EPI_RELU;
 }
 
+template <typename T, int FTH, int FTW>
+static void launch_flow7x7(const pfb_conv_params* p, cudaStream_t s) {
+  dim3 grid(ceil_div(p->W, FTW) * ceil_div(p->H, FTH) * p->B, ceil_div(p->Cout, 128));
+  conv_flow7x7_kernel<T, FTH, FTW><<<grid, 128, 0, s>>>((const float*)p->src[0].ptr, p->B, p->H, p->W, (const T*)p->weight, p->Cout,
+                                                        p->Cout_pad, p->bias, (T*)p->out, p->out_stride, p->out_offset);
+}
+
 int conv_flow7x7(const pfb_conv_params* p, cudaStream_t s) {
-  dim3 grid(ceil_div(p->W, kFTW) * ceil_div(p->H, kFTH) * p->B, ceil_div(p->Cout, 128));
   ProfScope prof(KC_CONV, s);
-  if (p->dtype == PFB_F16)
-    conv_flow7x7_kernel<__half><<<grid, 128, 0, s>>>((const float*)p->src[0].ptr, p->B, p->H, p->W, (const __half*)p->weight, p->Cout,
-                                                     p->Cout_pad, p->bias, (__half*)p->out, p->out_stride, p->out_offset);
-  else
-    conv_flow7x7_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>((const float*)p->src[0].ptr, p->B, p->H, p->W, (const __nv_bfloat16*)p->weight,
-                                                            p->Cout, p->Cout_pad, p->bias, (__nv_bfloat16*)p->out, p->out_stride,
-                                                            p->out_offset);
+  const bool rows = (p->W % 128) == 0;  // full-row tiles: no padded columns and a block count that fills whole waves
+  if (p->dtype == PFB_F16) {
+    if (rows) launch_flow7x7<__half, 1, 128>(p, s); else launch_flow7x7<__half, 8, 16>(p, s);
+  } else {
+    if (rows) launch_flow7x7<__nv_bfloat16, 1, 128>(p, s); else launch_flow7x7<__nv_bfloat16, 8, 16>(p, s);
+  }
   PFB_LAUNCH_CHECK();
   return PFB_OK;
 }

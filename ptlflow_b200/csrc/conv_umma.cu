@@ -17,17 +17,21 @@
 // chosen per shape to minimise padding (128x1 rows for W = 128: 440 tiles = 2.97 waves of 148 SMs).
 // The epilogue fuses bias + ReLU / sigmoid / tanh + the GRU gate arithmetic of
 // ptlflow/models/raft/update.py:58-73 and writes pixel-major f16/bf16 with 16-byte stores.
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace pfb {
 using namespace sm100;
 
 constexpr int kATileBytes = 128 * 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxAStages = 6, kMaxBStages = 8;
 
 struct __align__(8) ConvBars {
-  uint64_t full[kMaxStages];
-  uint64_t empty[kMaxStages];
+  uint64_t a_full[kMaxAStages];
+  uint64_t a_empty[kMaxAStages];
+  uint64_t b_full[kMaxBStages];
+  uint64_t b_empty[kMaxBStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
@@ -44,7 +48,13 @@ struct ConvUmmaArgs {
   int tiles_x, tiles_y, n_work;  // work items = tiles_x * tiles_y * B * n_tiles
   int acc_stride;                // TMEM column offset between the two accumulators
   int Cout, Cout_pad_k;
-  int stages, stage_bytes;
+  // Two rings: activation patches (A) and weight tiles (B).  With row tiles (TH == 1, "halo" mode) one A patch of
+  // TW + KW - 1 pixels serves all KW horizontal taps of a (chunk, ky): tap kx reads it through a descriptor whose
+  // start address is advanced by kx pixel rows (128 B each) -- the swizzle is a function of the absolute shared-memory
+  // address, so TMA writes and UMMA reads stay consistent.  Otherwise every tap loads its own patch.
+  int halo;
+  int a_stages, a_slot_bytes, a_tx_bytes, b_stages, b_slot_bytes;
+  int desc_base_offset_mode;     // experiment knob: 1 = put (addr >> 7) & 7 into the descriptor base_offset field
   const float* bias;
   int epilogue;
   float scale;
@@ -106,19 +116,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW, const ConvUmmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  ConvBars* bars = reinterpret_cast<ConvBars*>(smem + a.stages * a.stage_bytes);
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + a.a_stages * a.a_slot_bytes;
+  ConvBars* bars = reinterpret_cast<ConvBars*>(smemB + a.b_stages * a.b_slot_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int chunks_per_tap = 0;
-  for (int s = 0; s < a.nsrc; ++s) chunks_per_tap += a.src_chunks[s];
-  const int taps = a.KH * a.KW;
-  const int ksteps = taps * chunks_per_tap;
+  int chunks = 0;
+  for (int s = 0; s < a.nsrc; ++s) chunks += a.src_chunks[s];
   const int tiles_m = a.tiles_x * a.tiles_y * a.B;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
+    for (int s = 0; s < a.a_stages; ++s) {
+      mbar_init(&bars->a_full[s], 1);
+      mbar_init(&bars->a_empty[s], 1);
+    }
+    for (int s = 0; s < a.b_stages; ++s) {
+      mbar_init(&bars->b_full[s], 1);
+      mbar_init(&bars->b_empty[s], 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bars->acc_full[t], 1);
@@ -153,23 +167,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // ================= TMA producer =================
     if (lane == 0) {
       const int ph2 = a.KH >> 1, pw2 = a.KW >> 1;
-      const uint32_t tx = kATileBytes + a.NT * 128;
-      int it = 0;
+      const uint32_t btx = a.NT * 128;
+      int ia = 0, ib = 0;
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
         int n0, b, y0, x0;
         decode(w, n0, b, y0, x0);
-        for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / a.KW - ph2, dx = tap % a.KW - pw2;
-          int kidx = 0;
-          for (int s = 0; s < a.nsrc; ++s) {
-            const CUtensorMap* tm = s == 0 ? &tm0 : (s == 1 ? &tm1 : &tm2);
-            for (int c = 0; c < a.src_chunks[s]; ++c, ++kidx, ++it) {
-              const int st = it % a.stages, use = it / a.stages;
-              uint8_t* sa = smem + st * a.stage_bytes;
-              mbar_wait(&bars->empty[st], (use & 1) ^ 1);
-              mbar_arrive_expect_tx(&bars->full[st], tx);
-              tma_load_4d(sa, tm, &bars->full[st], a.src_coff[s] + c * 64, x0 + dx, y0 + dy, b);
-              tma_load_2d(sa + kATileBytes, &tmW, &bars->full[st], kidx * 64, tap * a.Cout_pad_k + n0);
+        int kidx = 0;
+        for (int s = 0; s < a.nsrc; ++s) {
+          const CUtensorMap* tm = s == 0 ? &tm0 : (s == 1 ? &tm1 : &tm2);
+          for (int c = 0; c < a.src_chunks[s]; ++c, ++kidx) {
+            for (int ky = 0; ky < a.KH; ++ky) {
+              for (int kx = 0; kx < a.KW; ++kx) {
+                if (kx == 0 || !a.halo) {  // activation patch: once per (chunk, ky) in halo mode, else once per tap
+                  const int st = ia % a.a_stages, use = ia / a.a_stages;
+                  ++ia;
+                  mbar_wait(&bars->a_empty[st], (use & 1) ^ 1);
+                  mbar_arrive_expect_tx(&bars->a_full[st], a.a_tx_bytes);
+                  tma_load_4d(smemA + st * a.a_slot_bytes, tm, &bars->a_full[st], a.src_coff[s] + c * 64,
+                              x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
+                }
+                const int st = ib % a.b_stages, use = ib / a.b_stages;
+                ++ib;
+                mbar_wait(&bars->b_empty[st], (use & 1) ^ 1);
+                mbar_arrive_expect_tx(&bars->b_full[st], btx);
+                tma_load_2d(smemB + st * a.b_slot_bytes, &tmW, &bars->b_full[st], kidx * 64, (ky * a.KW + kx) * a.Cout_pad_k + n0);
+              }
             }
           }
         }
@@ -179,22 +201,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, a.NT, a.ab_fmt);
-      int it = 0, i = 0;
+      int ia = 0, ib = 0, i = 0;
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++i) {
         const int t = i & 1, tuse = i >> 1;
         mbar_wait(&bars->acc_empty[t], (tuse & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + t * a.acc_stride;
-        for (int k = 0; k < ksteps; ++k, ++it) {
-          const int st = it % a.stages, use = it / a.stages;
-          uint8_t* sa = smem + st * a.stage_bytes;
-          mbar_wait(&bars->full[st], use & 1);
-          tc_fence_after();
-          const uint64_t da = make_desc_k_sw128(smem_u32(sa));
-          const uint64_t db = make_desc_k_sw128(smem_u32(sa + kATileBytes));
+        bool first = true;
+        for (int c = 0; c < chunks; ++c) {
+          for (int ky = 0; ky < a.KH; ++ky) {
+            int sta = 0;
+            for (int kx = 0; kx < a.KW; ++kx) {
+              if (kx == 0 || !a.halo) {
+                sta = ia % a.a_stages;
+                const int use = ia / a.a_stages;
+                ++ia;
+                mbar_wait(&bars->a_full[sta], use & 1);
+              }
+              const int stb = ib % a.b_stages, useb = ib / a.b_stages;
+              ++ib;
+              mbar_wait(&bars->b_full[stb], useb & 1);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(smemA + sta * a.a_slot_bytes) + (a.halo ? kx * 128 : 0);
+              uint64_t da = make_desc_k_sw128(a_addr);
+              if (a.desc_base_offset_mode) da |= (uint64_t)((a_addr >> 7) & 7) << 49;
+              const uint64_t db = make_desc_k_sw128(smem_u32(smemB + stb * a.b_slot_bytes));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16(d, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, (k | kk) != 0);
-          umma_commit(&bars->empty[st]);
+              for (int kk = 0; kk < 4; ++kk) {
+                umma_f16(d, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, !(first && kk == 0));
+              }
+              first = false;
+              umma_commit(&bars->b_empty[stb]);
+              if (!a.halo || kx == a.KW - 1) umma_commit(&bars->a_empty[sta]);
+            }
+          }
         }
         umma_commit(&bars->acc_full[t]);
       }
@@ -387,6 +427,11 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   ConvUmmaArgs a{};
   CUtensorMap tms[3];
   pick_tile(p->H, p->W, a.TW, a.TH);
+  static const int env_halo = getenv("PFB_CONV_HALO") ? atoi(getenv("PFB_CONV_HALO")) : 1;
+  static const int env_desc = getenv("PFB_UMMA_DESC_MODE") ? atoi(getenv("PFB_UMMA_DESC_MODE")) : 0;
+  a.halo = (env_halo && a.TH == 1 && p->KW > 1) ? 1 : 0;
+  a.desc_base_offset_mode = env_desc;
+  const int patch_w = a.TW + (a.halo ? p->KW - 1 : 0);
   a.tw_shift = 0;
   while ((1 << a.tw_shift) < a.TW) ++a.tw_shift;
   a.nsrc = p->nsrc;
@@ -397,7 +442,7 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
     // dim 0 ends at the source's last real channel: a partial last 64-chunk is zero-filled by the TMA unit
     uint64_t dims[4] = {(uint64_t)(src.offset + src.channels), (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)src.stride * 2, (uint64_t)p->W * src.stride * 2, (uint64_t)p->H * p->W * src.stride * 2};
-    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    uint32_t box[4] = {64, (uint32_t)patch_w, (uint32_t)a.TH, 1};
     int rc = make_tensor_map(&tms[i], src.ptr, p->dtype, 4, dims, str, box);
     if (rc) return rc;
   }
@@ -418,14 +463,24 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.tiles_y = ceil_div(p->H, a.TH);
   a.n_work = a.tiles_x * a.tiles_y * p->B * a.n_tiles;
   a.Cout = p->Cout; a.Cout_pad_k = p->Cout_pad_k;
-  a.stage_bytes = kATileBytes + a.NT * 128;
-  a.stages = (212 * 1024) / a.stage_bytes;
-  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  a.a_tx_bytes = patch_w * a.TH * 128;
+  a.a_slot_bytes = (int)align_up((size_t)a.a_tx_bytes, 1024);
+  a.b_slot_bytes = a.NT * 128;
+  {
+    // split ~212 KB between the rings: in halo mode one A patch feeds KW weight tiles, so B gets the depth
+    const int budget = 212 * 1024;
+    a.a_stages = a.halo ? 3 : 4;
+    a.b_stages = (budget - a.a_stages * a.a_slot_bytes) / a.b_slot_bytes;
+    if (a.b_stages > kMaxBStages) a.b_stages = kMaxBStages;
+    if (a.b_stages < 2) a.b_stages = 2;
+    int spare = budget - a.b_stages * a.b_slot_bytes - a.a_stages * a.a_slot_bytes;
+    while (spare >= a.a_slot_bytes && a.a_stages < kMaxAStages) { ++a.a_stages; spare -= a.a_slot_bytes; }
+  }
   a.bias = p->bias; a.epilogue = p->epilogue; a.scale = p->scale;
   a.out = p->out; a.out_stride = p->out_stride; a.out_offset = p->out_offset;
   a.aux_h = p->aux_h; a.aux_z = p->aux_z; a.hidden = p->hidden; a.flow = p->flow;
   a.ab_fmt = p->dtype == PFB_F16 ? 0 : 1;
-  const size_t smem = (size_t)a.stages * a.stage_bytes + sizeof(ConvBars) + 1024;
+  const size_t smem = (size_t)a.a_stages * a.a_slot_bytes + (size_t)a.b_stages * a.b_slot_bytes + sizeof(ConvBars) + 1024;
   dim3 grid(a.n_work < sm_count() ? a.n_work : sm_count());
   ProfScope prof(KC_CONV, s);
   if (p->dtype == PFB_F16) return launch_conv_umma<__half>(tms, tmW, a, grid, smem, s);
