@@ -70,7 +70,7 @@ UMMA_CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", UMMA_CONV_CASES, ids=[c[0] for c in UMMA_CONV_CASES])
-@pytest.mark.parametrize("b,h,w", [(2, 11, 21), (1, 16, 32)])
+@pytest.mark.parametrize("b,h,w", [(2, 11, 21), (1, 16, 32), (1, 5, 128), (2, 3, 200)])  # W >= 128: row tiles + halo reuse
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_conv_umma_relu_linear(case, b, h, w, dtype):
     from ptlflow_b200 import _lib, ops
@@ -101,11 +101,12 @@ def test_conv_umma_relu_linear(case, b, h, w, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("kh,kw", [(1, 5), (5, 1)])
-def test_conv_umma_gru_epilogues(dtype, kh, kw):
+@pytest.mark.parametrize("h,w", [(13, 19), (6, 128)])
+def test_conv_umma_gru_epilogues(dtype, kh, kw, h, w):
     """z|r fused GEMM (N = 256) + q GEMM with the gate arithmetic of update.py:58-73 in the epilogue."""
     from ptlflow_b200 import _lib, ops
 
-    b, h, w, hd = 2, 13, 19, 128
+    b, hd = 2, 128
     convz, convr, convq = (_make_conv(384, 128, kh, kw, s) for s in (21, 22, 23))
     net = torch.tanh(torch.from_numpy(synth.synth_normal("g/net", (b, hd, h, w), 3)))
     inp = torch.relu(torch.from_numpy(synth.synth_normal("g/inp", (b, 128, h, w), 3)))
