@@ -168,7 +168,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     if (lane == 0) {
       const int ph2 = a.KH >> 1, pw2 = a.KW >> 1;
       const uint32_t btx = a.NT * 128;
-      int ia = 0, ib = 0;
+      // ring positions advance incrementally (stage index + phase bit): no integer division on the issue path
+      int sta = 0, stb = 0;
+      uint32_t pha = 0, phb = 0;
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
         int n0, b, y0, x0;
         decode(w, n0, b, y0, x0);
@@ -176,21 +178,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         for (int s = 0; s < a.nsrc; ++s) {
           const CUtensorMap* tm = s == 0 ? &tm0 : (s == 1 ? &tm1 : &tm2);
           for (int c = 0; c < a.src_chunks[s]; ++c, ++kidx) {
+            int wrow = 0;  // (ky * KW + kx) * Cout_pad_k
             for (int ky = 0; ky < a.KH; ++ky) {
               for (int kx = 0; kx < a.KW; ++kx) {
                 if (kx == 0 || !a.halo) {  // activation patch: once per (chunk, ky) in halo mode, else once per tap
-                  const int st = ia % a.a_stages, use = ia / a.a_stages;
-                  ++ia;
-                  mbar_wait(&bars->a_empty[st], (use & 1) ^ 1);
-                  mbar_arrive_expect_tx(&bars->a_full[st], a.a_tx_bytes);
-                  tma_load_4d(smemA + st * a.a_slot_bytes, tm, &bars->a_full[st], a.src_coff[s] + c * 64,
+                  mbar_wait(&bars->a_empty[sta], pha ^ 1);
+                  mbar_arrive_expect_tx(&bars->a_full[sta], a.a_tx_bytes);
+                  tma_load_4d(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
                               x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
+                  if (++sta == a.a_stages) { sta = 0; pha ^= 1; }
                 }
-                const int st = ib % a.b_stages, use = ib / a.b_stages;
-                ++ib;
-                mbar_wait(&bars->b_empty[st], (use & 1) ^ 1);
-                mbar_arrive_expect_tx(&bars->b_full[st], btx);
-                tma_load_2d(smemB + st * a.b_slot_bytes, &tmW, &bars->b_full[st], kidx * 64, (ky * a.KW + kx) * a.Cout_pad_k + n0);
+                mbar_wait(&bars->b_empty[stb], phb ^ 1);
+                mbar_arrive_expect_tx(&bars->b_full[stb], btx);
+                tma_load_2d(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0);
+                wrow += a.Cout_pad_k;
+                if (++stb == a.b_stages) { stb = 0; phb ^= 1; }
               }
             }
           }
@@ -201,7 +203,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, a.NT, a.ab_fmt);
-      int ia = 0, ib = 0, i = 0;
+      int sa_next = 0, stb = 0, i = 0;
+      uint32_t pha = 0, phb = 0;
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++i) {
         const int t = i & 1, tuse = i >> 1;
         mbar_wait(&bars->acc_empty[t], (tuse & 1) ^ 1);
@@ -213,14 +216,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             int sta = 0;
             for (int kx = 0; kx < a.KW; ++kx) {
               if (kx == 0 || !a.halo) {
-                sta = ia % a.a_stages;
-                const int use = ia / a.a_stages;
-                ++ia;
-                mbar_wait(&bars->a_full[sta], use & 1);
+                sta = sa_next;
+                mbar_wait(&bars->a_full[sta], pha);
+                if (++sa_next == a.a_stages) { sa_next = 0; pha ^= 1; }
               }
-              const int stb = ib % a.b_stages, useb = ib / a.b_stages;
-              ++ib;
-              mbar_wait(&bars->b_full[stb], useb & 1);
+              mbar_wait(&bars->b_full[stb], phb);
               tc_fence_after();
               const uint32_t a_addr = smem_u32(smemA + sta * a.a_slot_bytes) + (a.halo ? kx * 128 : 0);
               uint64_t da = make_desc_k_sw128(a_addr);
@@ -233,6 +233,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
               first = false;
               umma_commit(&bars->b_empty[stb]);
               if (!a.halo || kx == a.KW - 1) umma_commit(&bars->a_empty[sta]);
+              if (++stb == a.b_stages) { stb = 0; phb ^= 1; }
             }
           }
         }
