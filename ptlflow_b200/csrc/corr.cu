@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(LevelTable lv, const f
 // Fast path (radius <= 4, levels <= 4, pixel-major output): every lane issues the gathers of ALL levels
 // before any is consumed (16 independent loads in flight per lane instead of 4 dependent rounds), the four
 // windows live side by side in shared memory, and the L*(2r+1)^2 outputs are written as one coalesced run.
-template <typename T, typename TO>
+template <typename T, typename TO, int R>
 __global__ void __launch_bounds__(128) corr_lookup_r4_kernel(LevelTable lv, const float* __restrict__ coords,
-                                                             TO* __restrict__ out, int nq, int levels, int r,
-                                                             int out_stride) {
+                                                             TO* __restrict__ out, int nq, int levels, int out_stride) {
   __shared__ float smem[4][4 * 100];
   __shared__ float wts[4][4][4];
-  const int D = 2 * r + 2, K = 2 * r + 1, DD = D * D, KK = K * K;
+  // compile-time radius: every index division below becomes a multiply-shift
+  constexpr int r = R, D = 2 * R + 2, K = 2 * R + 1, DD = D * D, KK = K * K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* win = smem[warp];
   const int q = blockIdx.x * 4 + warp;
@@ -412,13 +412,18 @@ static int launch_lookup_t(const LevelTable& lv, const float* coords, void* out,
   size_t smem = (size_t)warps * D * D * sizeof(float);
   dim3 grid(ceil_div(nq, warps));
   ProfScope prof(KC_LOOKUP, s);
-  if (!nchw && radius <= 4 && levels <= 4) {
-    if (out_dtype == PFB_F32)
-      corr_lookup_r4_kernel<T, float><<<grid, 128, 0, s>>>(lv, coords, (float*)out, nq, levels, radius, out_stride);
-    else if (out_dtype == PFB_F16)
-      corr_lookup_r4_kernel<T, __half><<<grid, 128, 0, s>>>(lv, coords, (__half*)out, nq, levels, radius, out_stride);
-    else
-      corr_lookup_r4_kernel<T, __nv_bfloat16><<<grid, 128, 0, s>>>(lv, coords, (__nv_bfloat16*)out, nq, levels, radius, out_stride);
+  if (!nchw && (radius == 4 || radius == 3) && levels <= 4) {
+#define PFB_LOOKUP_FAST(TO, R) corr_lookup_r4_kernel<T, TO, R><<<grid, 128, 0, s>>>(lv, coords, (TO*)out, nq, levels, out_stride)
+    if (radius == 4) {
+      if (out_dtype == PFB_F32) PFB_LOOKUP_FAST(float, 4);
+      else if (out_dtype == PFB_F16) PFB_LOOKUP_FAST(__half, 4);
+      else PFB_LOOKUP_FAST(__nv_bfloat16, 4);
+    } else {
+      if (out_dtype == PFB_F32) PFB_LOOKUP_FAST(float, 3);
+      else if (out_dtype == PFB_F16) PFB_LOOKUP_FAST(__half, 3);
+      else PFB_LOOKUP_FAST(__nv_bfloat16, 3);
+    }
+#undef PFB_LOOKUP_FAST
     PFB_LAUNCH_CHECK();
     return PFB_OK;
   }
