@@ -38,38 +38,58 @@ __global__ void preprocess_frames_kernel(const T* __restrict__ img, T* __restric
 
 // ---- instance norm ---------------------------------------------------------------------------------
 // stats: [B][C][2] doubles (sum, sum of squares), zeroed by the caller-side memset node.
+// thread -> (channel octet, pixel lane): 16-byte loads, consecutive threads on consecutive octets (coalesced);
+// per-thread fp32 partials over a few dozen pixels -> shared-memory fp32 atomics per block -> fp64 global atomics.
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = to_f32(h[i]);
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) inorm_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, int HW, int C,
                                                           int pix_per_block) {
-  // thread -> (channel pair, pixel lane): consecutive threads read consecutive channels (coalesced)
+  extern __shared__ float acc[];  // [2][C]
   const int b = blockIdx.y;
-  const int c2n = C / 2;                       // channel pairs
-  const int lanes = blockDim.x / c2n;          // pixel lanes per block
-  const int cp = threadIdx.x % c2n, pl = threadIdx.x / c2n;
-  const bool active = pl < lanes;  // trailing threads (blockDim not a multiple of C/2) only take part in the barrier
+  const int c8n = C / 8;
+  const int lanes = blockDim.x / c8n;
+  const int co = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, HW);
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  const T* base = x + (size_t)b * HW * C + 2 * cp;
-  for (int p = p0 + pl; active && p < p1; p += lanes) {
-    const T* v = base + (size_t)p * C;
-    float a = to_f32(v[0]), bb = to_f32(v[1]);
-    s0 += a; q0 = fmaf(a, a, q0);
-    s1 += bb; q1 = fmaf(bb, bb, q1);
-  }
-  extern __shared__ float red[];  // [4][blockDim.x]
-  red[threadIdx.x] = s0; red[blockDim.x + threadIdx.x] = q0;
-  red[2 * blockDim.x + threadIdx.x] = s1; red[3 * blockDim.x + threadIdx.x] = q1;
-  __syncthreads();
-  if (active && pl == 0) {
-    double ds0 = 0, dq0 = 0, ds1 = 0, dq1 = 0;
-    for (int l = 0; l < lanes; ++l) {
-      const int t = l * c2n + cp;
-      ds0 += red[t]; dq0 += red[blockDim.x + t]; ds1 += red[2 * blockDim.x + t]; dq1 += red[3 * blockDim.x + t];
+  float s[8], q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+  if (pl < lanes) {
+    const T* base = x + (size_t)b * HW * C + 8 * co;
+#pragma unroll 4
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      float v[8];
+      load8<T>(base + (size_t)p * C, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s[k] += v[k];
+        q[k] = fmaf(v[k], v[k], q[k]);
+      }
     }
-    double* st = stats + ((size_t)b * C + 2 * cp) * 2;
-    atomicAdd(st + 0, ds0); atomicAdd(st + 1, dq0);
-    atomicAdd(st + 2, ds1); atomicAdd(st + 3, dq1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&acc[8 * co + k], s[k]);
+      atomicAdd(&acc[C + 8 * co + k], q[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int c = i % C, which = i / C;
+    atomicAdd(stats + ((size_t)b * C + c) * 2 + which, (double)acc[i]);
   }
 }
 
@@ -189,13 +209,11 @@ extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void*
   float2* ss = reinterpret_cast<float2*>(stats + (size_t)B * C * 2);
   PFB_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(double), s));
   const int threads = 256;
-  int slabs = ceil_div(4 * sm_count(), B);
-  if (slabs > ceil_div(HW, 64)) slabs = ceil_div(HW, 64);
-  if (slabs < 1) slabs = 1;
-  const int ppb = ceil_div(HW, slabs);
+  PFB_CHECK_ARG(B <= 65535, "instance_norm_act: batch too large");
+  const int ppb = HW >= 8192 ? 1024 : (HW >= 1024 ? 256 : 64);  // pixels per block: plenty of blocks, few global atomics
   dim3 grid(ceil_div(HW, ppb), B);
   ProfScope prof(KC_MISC, s);
-  PFB_DISPATCH_DTYPE(dtype, T, { inorm_stats_kernel<T><<<grid, threads, 4 * threads * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb); });
+  PFB_DISPATCH_DTYPE(dtype, T, { inorm_stats_kernel<T><<<grid, threads, 2 * C * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb); });
   PFB_LAUNCH_CHECK();
   inorm_finalize_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(stats, ss, B * C, HW, eps);
   PFB_LAUNCH_CHECK();
