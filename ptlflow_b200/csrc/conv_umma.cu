@@ -201,41 +201,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     }
   } else if (warp == 5) {
     // ================= MMA issuer =================
+    // One thread issues everything, so its instruction count per tap IS the pacing of the tensor pipe when the
+    // tile is small (ncu: ~130 SASS instructions/tap at ~8 clk each paced the first version).  Everything that can
+    // be precomputed is: 32-bit shared addresses of barriers and slots, descriptor words updated by adds only.
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, a.NT, a.ab_fmt);
-      int sa_next = 0, stb = 0, i = 0;
+      // descriptor = {lo: (addr >> 4) | LBO(1) << 16, hi: SBO(1024 >> 4) | version 1 << 14 | SWIZZLE_128B 2 << 29}
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_slot16 = (uint32_t)a.a_slot_bytes >> 4, b_slot16 = (uint32_t)a.b_slot_bytes >> 4;
+      const uint32_t a_lo0 = ((smem_u32(smemA) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((smem_u32(smemB) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
+      const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
+      const int kw_halo = a.halo ? a.KW : 1;             // taps served by one activation patch
+      const int groups = chunks * a.KH * (a.halo ? 1 : a.KW);  // activation patches per tile
+      int sa = 0, sb = 0, i = 0;
       uint32_t pha = 0, phb = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
       for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++i) {
-        const int t = i & 1, tuse = i >> 1;
-        mbar_wait(&bars->acc_empty[t], (tuse & 1) ^ 1);
+        const int t = i & 1;
+        mbar_wait(&bars->acc_empty[t], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + t * a.acc_stride;
-        bool first = true;
-        for (int c = 0; c < chunks; ++c) {
-          for (int ky = 0; ky < a.KH; ++ky) {
-            int sta = 0;
-            for (int kx = 0; kx < a.KW; ++kx) {
-              if (kx == 0 || !a.halo) {
-                sta = sa_next;
-                mbar_wait(&bars->a_full[sta], pha);
-                if (++sa_next == a.a_stages) { sa_next = 0; pha ^= 1; }
-              }
-              mbar_wait(&bars->b_full[stb], phb);
-              tc_fence_after();
-              const uint32_t a_addr = smem_u32(smemA + sta * a.a_slot_bytes) + (a.halo ? kx * 128 : 0);
-              uint64_t da = make_desc_k_sw128(a_addr);
-              if (a.desc_base_offset_mode) da |= (uint64_t)((a_addr >> 7) & 7) << 49;
-              const uint64_t db = make_desc_k_sw128(smem_u32(smemB + stb * a.b_slot_bytes));
+        uint32_t acc = 0;  // first MMA of the tile overwrites the accumulator
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait_addr(bar_a_full + 8 * sa, pha);
+          for (int kx = 0; kx < kw_halo; ++kx) {
+            mbar_wait_addr(bar_b_full + 8 * sb, phb);
+            tc_fence_after();
+            const uint32_t al = a_lo + 8 * kx;  // halo: tap kx starts kx pixel rows (128 B) into the patch
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                umma_f16(d, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, !(first && kk == 0));
-              }
-              first = false;
-              umma_commit(&bars->b_empty[stb]);
-              if (!a.halo || kx == a.KW - 1) umma_commit(&bars->a_empty[sta]);
-              if (++stb == a.b_stages) { stb = 0; phb ^= 1; }
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16_lohi(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, acc);
+              acc = 1;
             }
+            umma_commit_addr(bar_b_empty + 8 * sb);
+            b_lo += b_slot16;
+            if (++sb == a.b_stages) { sb = 0; phb ^= 1; b_lo = b_lo0; }
           }
+          umma_commit_addr(bar_a_empty + 8 * sa);
+          a_lo += a_slot16;
+          if (++sa == a.a_stages) { sa = 0; pha ^= 1; a_lo = a_lo0; }
         }
         umma_commit(&bars->acc_full[t]);
       }
