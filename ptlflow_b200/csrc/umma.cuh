@@ -36,11 +36,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trapped kernel (cudaErrorLaunchFailure) instead of a hung GPU.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug becomes a trapped kernel (cudaErrorLaunchFailure) after ~2 s of wall time
+// instead of a hung GPU (try_wait itself may block for a system-dependent interval, so spins are not a clock).
+#define PFB_MBAR_TIMEOUT_NS 2000000000ull
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 0xFF) == 0 && global_timer_ns() - t0 > PFB_MBAR_TIMEOUT_NS) __trap();
   }
 }
 
@@ -106,19 +115,23 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, ui
 __device__ __forceinline__ void umma_commit_addr(uint32_t bar_smem_addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_smem_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_smem_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_smem_addr, uint32_t parity) {
+  if (mbar_try_wait_addr(bar_smem_addr, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar_smem_addr), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 26)) __trap();
+  while (!mbar_try_wait_addr(bar_smem_addr, parity)) {
+    if ((++spins & 0xFF) == 0 && global_timer_ns() - t0 > PFB_MBAR_TIMEOUT_NS) __trap();
   }
 }
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
