@@ -30,6 +30,7 @@ E2E_CASES = [
     ("e2e_raft_smooth_b2", "raft", dict(iters=12), 2, 128, 192, "smooth", 4, 14),
     ("e2e_raft_altcorr", "raft", dict(iters=4, alternate_corr=True), 1, 128, 160, "noise", 5, 15),
     ("e2e_raft_r3_l3", "raft", dict(iters=3, corr_radius=3, corr_levels=3), 1, 128, 136, "smooth", 6, 16),
+    ("e2e_gma", "gma", dict(iters=6), 2, 128, 192, "smooth", 7, 17),  # BASELINE.json configs[2] family
 ]
 
 
@@ -122,9 +123,9 @@ def make_ops() -> None:
     )
 
     # --- state_dict names/shapes (restore_model's strict load contract) ------------------
-    for variant in ("raft", "raft_small"):
-        mm = getattr(ref_raft, variant)()
-        shapes = {k: list(v.shape) for k, v in mm.state_dict().items() if k.split(".")[0] in ("fnet", "cnet", "update_block")}
+    for variant in ("raft", "raft_small", "gma"):
+        mm = getattr(ref_shim.load_gma() if variant == "gma" else ref_raft, variant)()
+        shapes = {k: list(v.shape) for k, v in mm.state_dict().items() if k.split(".")[0] in ("fnet", "cnet", "update_block", "att")}
         with open(os.path.join(GOLDEN_DIR, f"state_shapes_{variant}.json"), "w") as f:
             json.dump(shapes, f, indent=0)
         print("state_shapes", variant, len(shapes), sum(int(np.prod(s)) for k, s in shapes.items() if "running" not in k and "num_batches" not in k))

@@ -296,7 +296,37 @@ VARIANTS = {
     # name: (small, hidden, context, fnet_dim, cnet_norm, default_radius)
     "raft": (False, 128, 128, 256, "batch", 4),
     "raft_small": (True, 96, 64, 128, "none", 3),
+    "gma": (False, 128, 128, 256, "batch", 4),
 }
+
+
+# --------------------------------------------------------------------------------------
+# a13: GMA extras (content-only attention, num_heads = 1: the registered default)
+# --------------------------------------------------------------------------------------
+def gma_attention(inp: Tensor, sd: SD, p: str = "att.") -> Tensor:
+    """softmax_j( scale * q_i . k_j ), scale = dim_head^-1/2, q|k = to_qk(inp).  -> [B, N, N]
+    ptlflow/models/gma/gma_utils.py:58-76 (position_only = position_and_content = False)."""
+    b, c, h, w = inp.shape
+    qk = F.conv2d(inp, sd[p + "to_qk.weight"])
+    q, k = qk[:, :c].reshape(b, c, h * w), qk[:, c:].reshape(b, c, h * w)
+    sim = torch.bmm((q * c ** -0.5).transpose(1, 2), k)
+    return torch.softmax(sim, dim=-1)
+
+
+def gma_aggregate(attn: Tensor, fmap: Tensor, sd: SD, p: str = "update_block.aggregator.") -> Tensor:
+    """fmap + gamma * (attn @ to_v(fmap)).  ptlflow/models/gma/gma_utils.py:101-113 (heads = 1: no project)."""
+    b, c, h, w = fmap.shape
+    v = F.conv2d(fmap, sd[p + "to_v.weight"]).reshape(b, c, h * w)
+    out = torch.bmm(attn, v.transpose(1, 2)).transpose(1, 2).reshape(b, c, h, w)
+    return fmap + sd[p + "gamma"] * out
+
+
+def gma_update_block(net, inp, corr, flow, attn, sd: SD):
+    """-> (net, mask, delta_flow).  ptlflow/models/gma/update.py:148-160."""
+    motion = motion_encoder_basic(flow, corr, sd)
+    motion_global = gma_aggregate(attn, motion, sd)
+    net = sep_conv_gru(net, torch.cat([inp, motion, motion_global], 1), sd)
+    return net, mask_head(net, sd), flow_head(net, sd)
 
 
 def raft_forward(
@@ -334,13 +364,19 @@ def raft_forward(
             trace["pyramid"] = pyramid
 
     block = small_update_block if small else basic_update_block
+    attn = gma_attention(inp, sd) if variant == "gma" else None  # ptlflow/models/gma/gma.py:181
+    if trace is not None and attn is not None:
+        trace["attention"] = attn
     mask = None
     for _ in range(iters):
         if alternate_corr:
             corr = alt_corr_lookup(fmap1, fmap2, coords1, radius, corr_levels)
         else:
             corr = corr_lookup(pyramid, coords1, radius)
-        net, mask, delta = block(net, inp, corr, coords1 - coords0, sd)
+        if attn is not None:
+            net, mask, delta = gma_update_block(net, inp, corr, coords1 - coords0, attn, sd)
+        else:
+            net, mask, delta = block(net, inp, corr, coords1 - coords0, sd)
         coords1 = coords1 + delta
         if trace is not None:
             trace["lookups"].append(corr)
@@ -427,7 +463,7 @@ def state_dict_shapes(variant: str, corr_levels: int = 4, corr_radius: Optional[
         conv(e + "convf1", 128, 2, 7, 7)
         conv(e + "convf2", 64, 128, 3, 3)
         conv(e + "conv", 126, 256, 3, 3)
-        gin = hdim + 128 + hdim
+        gin = hdim + 128 + hdim + (128 if variant == "gma" else 0)
         for sfx, (kh, kw) in (("1", (1, 5)), ("2", (5, 1))):
             for nm in ("convz", "convr", "convq"):
                 conv(g + nm + sfx, hdim, gin, kh, kw)
@@ -435,4 +471,11 @@ def state_dict_shapes(variant: str, corr_levels: int = 4, corr_radius: Optional[
         conv(fh + "conv2", 2, 256, 3, 3)
         conv("update_block.mask.0", 256, 128, 3, 3)
         conv("update_block.mask.2", 576, 256, 1, 1)
+    if variant == "gma":
+        s["update_block.aggregator.gamma"] = (1,)
+        s["update_block.aggregator.to_v.weight"] = (128, 128, 1, 1)
+        s["att.to_qk.weight"] = (256, 128, 1, 1)
+        s["att.pos_emb.rel_ind"] = (160, 160)
+        s["att.pos_emb.rel_height.weight"] = (319, 128)
+        s["att.pos_emb.rel_width.weight"] = (319, 128)
     return s

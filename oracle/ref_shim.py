@@ -113,7 +113,7 @@ def build_reference_model(variant: str, seed: int = 0, **kwargs):
     new = {}
     for k, v in sd.items():
         if k.split(".")[0] in ("fnet", "cnet", "update_block", "att"):
-            new[k] = torch.from_numpy(synth.synth_tensor(k, tuple(v.shape), seed)).to(v.dtype)
+            new[k] = torch.from_numpy(synth.synth_tensor(k, tuple(v.shape), seed)).to(v.dtype).reshape(v.shape)
         else:
             new[k] = v
     model.load_state_dict(new)

@@ -32,6 +32,9 @@ def synth_tensor(name: str, shape: Tuple[int, ...], seed: int = 0) -> np.ndarray
     shape = tuple(int(s) for s in shape)
     if name.endswith("num_batches_tracked"):
         return np.zeros(shape, dtype=np.int64)
+    if name.endswith("rel_ind"):  # GMA RelPosEmb index buffer: deltas + max_pos - 1 (gma_utils.py:12-16), not random
+        n = shape[0]
+        return (np.arange(n)[None, :] - np.arange(n)[:, None] + n - 1).astype(np.int64)
     n = g.standard_normal(shape, dtype=np.float64)
     if name.endswith("running_var"):
         return (1.0 + 0.2 * np.abs(n)).astype(np.float32)
