@@ -118,8 +118,10 @@ typedef enum {
   PFB_EPI_GRU_Q = 3,   /* q = tanh(acc+bias); out = (1 - z) * h + z * q     update.py:63-64 */
   PFB_EPI_FLOW = 4,    /* Cout = 2: coords1 += acc + bias (fp32, in place);
                           out(fp32) = coords1 - grid               raft.py:174-178          */
-  PFB_EPI_RELU_APPEND_FLOW = 5 /* relu into cols [0,Cout) and copy flow(fp32 [.,2]) into the
+  PFB_EPI_RELU_APPEND_FLOW = 5, /* relu into cols [0,Cout) and copy flow(fp32 [.,2]) into the
                           next two columns                          update.py:111-112      */
+  PFB_EPI_AXPY = 6     /* out = residual + scale * (acc + bias); residual = aux_h[p * hidden + n]
+                          (GMA Aggregate: fmap + gamma * attn@v)    gma_utils.py:101-113   */
 } pfb_epilogue;
 
 typedef struct {
@@ -187,6 +189,12 @@ PFB_API int pfb_convex_upsample(const float* coords, const void* mask, float* ou
 PFB_API int pfb_upflow8(const float* coords, float* out, float* flow_small, int B, int H, int W, int out_h, int out_w,
                 int pad_top, int pad_left, pfb_stream stream);
 
+/* GMA attention: in-place softmax over the last axis of sim [rows, cols] (sim = pfb_corr_volume_build(q, k)
+ * level 0: <q, k> / sqrt(dim_head) is exactly the content attention logit).   gma_utils.py:58-76 */
+PFB_API int pfb_softmax_rows(void* x, size_t rows, int cols, pfb_dtype dtype, pfb_stream stream);
+/* [B, HW, C] pixel-major -> [B, C, HW_pad] (zero padded): K-major operand for the attn @ v GEMM */
+PFB_API int pfb_transpose_pm(const void* in, void* out, int B, int HW, int C, int HW_pad, pfb_dtype dtype, pfb_stream stream);
+
 /* cnet output [B,H,W,hd+cd] -> net = tanh(first hd), inp = relu(rest)     raft.py:155-158 */
 PFB_API int pfb_context_split(const void* cnet, void* net, void* inp, int B, int H, int W, int hidden, int context,
                       pfb_dtype dtype, pfb_stream stream);
@@ -201,6 +209,7 @@ typedef enum {
   PFB_L_CONVC1 = 0, PFB_L_CONVC2, PFB_L_CONVF1, PFB_L_CONVF2, PFB_L_CONV,
   PFB_L_GRU_ZR1, PFB_L_GRU_Q1, PFB_L_GRU_ZR2, PFB_L_GRU_Q2,
   PFB_L_FLOW1, PFB_L_FLOW2, PFB_L_MASK1, PFB_L_MASK2,
+  PFB_L_AGG_V, /* GMA Aggregate.to_v (1x1, no bias) */
   PFB_L_COUNT
 } pfb_layer_id;
 
@@ -214,7 +223,8 @@ typedef struct {
 
 typedef struct {
   int variant;        /* 0 = raft (BasicUpdateBlock, SepConvGRU, convex upsample)
-                         1 = raft_small (SmallUpdateBlock, ConvGRU, bilinear upflow8) */
+                         1 = raft_small (SmallUpdateBlock, ConvGRU, bilinear upflow8)
+                         2 = gma (GMAUpdateBlock: raft + per-iteration attention aggregate, gma/update.py:127-160) */
   pfb_dtype dtype;
   int B, H, W;        /* 1/8-resolution grid */
   int feat_dim;       /* C of fmap1/fmap2 (on-the-fly mode) */
@@ -240,6 +250,8 @@ typedef struct {
   float* flow_small;          /* [B,2,H,W] fp32 */
   void* workspace;            /* pfb_raft_workspace_bytes(cfg) */
   size_t workspace_bytes;
+  const void* attention;      /* gma: softmax attention [B, H*W, H*W] dtype (pfb_gma_attention_softmax) */
+  float agg_gamma;            /* gma: Aggregate.gamma */
 } pfb_raft_buffers;
 
 PFB_API size_t pfb_raft_workspace_bytes(const pfb_raft_cfg* cfg);

@@ -21,10 +21,10 @@ PFB_MAX_SRC = 4
 F32, F16, BF16 = 0, 1, 2
 _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
-EPI_LINEAR, EPI_RELU, EPI_GRU_ZR, EPI_GRU_Q, EPI_FLOW, EPI_RELU_APPEND_FLOW = range(6)
+EPI_LINEAR, EPI_RELU, EPI_GRU_ZR, EPI_GRU_Q, EPI_FLOW, EPI_RELU_APPEND_FLOW, EPI_AXPY = range(7)
 
 (L_CONVC1, L_CONVC2, L_CONVF1, L_CONVF2, L_CONV, L_GRU_ZR1, L_GRU_Q1, L_GRU_ZR2, L_GRU_Q2,
- L_FLOW1, L_FLOW2, L_MASK1, L_MASK2, L_COUNT) = range(14)
+ L_FLOW1, L_FLOW2, L_MASK1, L_MASK2, L_AGG_V, L_COUNT) = range(15)
 
 
 class ConvSrc(C.Structure):
@@ -70,6 +70,7 @@ class RaftBuffers(C.Structure):
         ("pyramid", C.POINTER(C.c_void_p)), ("fmap1", C.c_void_p), ("net", C.c_void_p), ("inp", C.c_void_p),
         ("coords", C.c_void_p), ("flow_up", C.c_void_p), ("flow_small", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("attention", C.c_void_p), ("agg_gamma", C.c_float),
     ]
 
 
@@ -94,6 +95,8 @@ SIGNATURES = {
     "pfb_pack_conv_weight_kmajor": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int), _I, _I, _I, _I, _S]),
     "pfb_convex_upsample": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_upflow8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _S]),
+    "pfb_softmax_rows": (_I, [_P, C.c_size_t, _I, _I, _S]),
+    "pfb_transpose_pm": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
     "pfb_context_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_init_coords": (_I, [_P, _P, _I, _I, _I, _S]),
     "pfb_raft_workspace_bytes": (C.c_size_t, [C.POINTER(RaftCfg)]),

@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvDev a) {
           reinterpret_cast<T*>(a.out)[(size_t)p * a.out_stride + a.out_offset + n] = from_f32<T>((1.f - z) * h + z * q);
           break;
         }
+        case PFB_EPI_AXPY: {
+          float res = to_f32(reinterpret_cast<const T*>(a.aux_h)[(size_t)p * hd + n]);
+          reinterpret_cast<T*>(a.out)[(size_t)p * a.out_stride + a.out_offset + n] = from_f32<T>(res + a.scale * v);
+          break;
+        }
         case PFB_EPI_FLOW: {
           // n in {0,1}: coords1 += delta ; flow = coords1 - coords0, coords0 = (x, y)
           float c1 = a.coords[(size_t)p * 2 + n] + v;
@@ -206,6 +211,9 @@ extern "C" PFB_API int pfb_conv2d(const pfb_conv_params* p, pfb_stream stream) {
   }
   switch (p->epilogue) {
     case PFB_EPI_LINEAR: case PFB_EPI_RELU: break;
+    case PFB_EPI_AXPY:
+      PFB_CHECK_ARG(p->aux_h && p->hidden >= p->Cout, "conv2d: AXPY needs aux_h (residual) with stride hidden >= Cout");
+      break;
     case PFB_EPI_GRU_ZR:
       PFB_CHECK_ARG(p->aux_h && p->aux_z && p->hidden > 0 && p->Cout == 2 * p->hidden, "conv2d: GRU_ZR needs aux_h, aux_z and Cout == 2*hidden");
       break;

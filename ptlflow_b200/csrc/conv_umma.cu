@@ -273,7 +273,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 8; ++q) bb[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint4 hraw[4], zraw[4];
-        const bool need_h = ok && ((a.epilogue == PFB_EPI_GRU_ZR && n >= hd) || a.epilogue == PFB_EPI_GRU_Q);
+        const bool need_h = ok && ((a.epilogue == PFB_EPI_GRU_ZR && n >= hd) || a.epilogue == PFB_EPI_GRU_Q ||
+                                   (a.epilogue == PFB_EPI_AXPY && n + 32 <= a.Cout));
         const bool need_z = ok && a.epilogue == PFB_EPI_GRU_Q;
         if (need_h) {
           const T* hp = reinterpret_cast<const T*>(a.aux_h) + p * hd + (a.epilogue == PFB_EPI_GRU_ZR ? n - hd : n);
@@ -306,6 +307,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           case PFB_EPI_RELU: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+            store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            break;
+          }
+          case PFB_EPI_AXPY: {  // residual + scale * acc   (residual = aux_h[p * hidden + n])
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float h[8];
+              unpack8<T>(hraw[q], h);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[8 * q + e] = h[e] + a.scale * v[8 * q + e];
+            }
             store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
@@ -390,6 +402,9 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
   if (cin_pad != p->Cin_pad) return false;
   switch (p->epilogue) {
     case PFB_EPI_LINEAR: case PFB_EPI_RELU: case PFB_EPI_RELU_APPEND_FLOW: break;
+    case PFB_EPI_AXPY:
+      if (!p->aux_h || p->hidden % 8 || p->Cout % 32) return false;
+      break;
     case PFB_EPI_GRU_ZR:
       if (p->hidden % 32 || p->Cout_pad_k != 2 * p->hidden || p->Cout_pad_k > 256) return false;
       break;

@@ -167,6 +167,48 @@ __global__ void upflow8_kernel(const float* __restrict__ coords, float* __restri
   }
 }
 
+// in-place softmax over rows of length `cols` (one block per row, fp32 math)   gma_utils.py:74
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(T* __restrict__ x, int cols) {
+  __shared__ float red[8];
+  T* row = x + (size_t)blockIdx.x * cols;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, to_f32(row[c]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += expf(to_f32(row[c]) - m);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) row[c] = from_f32<T>(expf(to_f32(row[c]) - m) * inv);
+}
+
+// [B][HW][C] -> [B][C][HW_pad], zero fill for hw >= HW (32x32 smem tile transpose)
+template <typename T>
+__global__ void transpose_pm_kernel(const T* __restrict__ in, T* __restrict__ out, int HW, int C, int HW_pad) {
+  __shared__ T tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? in[((size_t)b * HW + p) * C + c] : from_f32<T>(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW_pad) out[((size_t)b * C + c) * HW_pad + p] = tile[threadIdx.x][i];
+  }
+}
+
 int launch_flow_from_coords(const float* coords, float* flow, int B, int H, int W, cudaStream_t s) {
   const int P = B * H * W;
   ProfScope prof(KC_MISC, s);
@@ -276,4 +318,24 @@ extern "C" PFB_API int pfb_upflow8(const float* coords, float* out, float* flow_
   }
   PFB_LAUNCH_CHECK();
   return write_flow_small(coords, flow_small, B, H, W, s);
+}
+
+extern "C" PFB_API int pfb_softmax_rows(void* x, size_t rows, int cols, pfb_dtype dtype, pfb_stream stream) {
+  PFB_CHECK_ARG(x && rows > 0 && rows < (1ull << 31) && cols > 0 && dtype_ok(dtype), "softmax_rows: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  ProfScope prof(KC_MISC, s);
+  PFB_DISPATCH_DTYPE(dtype, T, { softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, s>>>((T*)x, cols); });
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}
+
+extern "C" PFB_API int pfb_transpose_pm(const void* in, void* out, int B, int HW, int C, int HW_pad, pfb_dtype dtype,
+                                        pfb_stream stream) {
+  PFB_CHECK_ARG(in && out && B > 0 && B <= 65535 && HW > 0 && C > 0 && HW_pad >= HW && dtype_ok(dtype), "transpose_pm: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  dim3 grid(ceil_div(HW_pad, 32), ceil_div(C, 32), B), block(32, 8);
+  ProfScope prof(KC_MISC, s);
+  PFB_DISPATCH_DTYPE(dtype, T, { transpose_pm_kernel<T><<<grid, block, 0, s>>>((const T*)in, (T*)out, HW, C, HW_pad); });
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
 }

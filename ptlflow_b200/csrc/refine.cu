@@ -16,6 +16,8 @@ struct Workspace {
   // element strides (channels per pixel) and byte offsets inside the caller's workspace
   int planes, corr_stride;
   size_t off_corr, off_cor1, off_corflo, off_flo1, off_motion, off_z, off_rh, off_fh, off_mh, off_mask, off_flow;
+  size_t off_vbuf, off_vT;  // gma: to_v(motion) [P][128] and its per-sample transpose [B][128][n_pad]
+  int n_pad;
   size_t total;
   int c_cor1, c_corflo, c_cor2, c_flo1, c_flo2, c_motion, c_fh;
 };
@@ -28,8 +30,10 @@ static Workspace plan(const pfb_raft_cfg* c) {
   w.planes = c->corr_levels * K * K;
   // tensor-core path wants 64-channel (128-byte) K chunks; pad columns are zero-filled by the lookup
   w.corr_stride = (c->dtype == PFB_F32) ? w.planes : (int)align_up(w.planes, 64);
-  if (c->variant == 0) {
-    w.c_cor1 = 256; w.c_cor2 = 192; w.c_flo1 = 128; w.c_flo2 = 64; w.c_motion = 128; w.c_fh = 256;
+  if (c->variant == 0 || c->variant == 2) {
+    w.c_cor1 = 256; w.c_cor2 = 192; w.c_flo1 = 128; w.c_flo2 = 64; w.c_fh = 256;
+    // gma keeps [motion | motion_global] side by side so the GRU still sees three sources (update.py:150-151)
+    w.c_motion = c->variant == 2 ? 256 : 128;
   } else {
     w.c_cor1 = 0; w.c_cor2 = 96; w.c_flo1 = 64; w.c_flo2 = 32; w.c_motion = 82; w.c_fh = 128;
   }
@@ -44,16 +48,19 @@ static Workspace plan(const pfb_raft_cfg* c) {
   w.off_z = take(P * (size_t)c->hidden_dim * es);
   w.off_rh = take(P * (size_t)c->hidden_dim * es);
   w.off_fh = take(P * (size_t)w.c_fh * es);
-  w.off_mh = take(c->variant == 0 ? P * 256 * es : 0);
-  w.off_mask = take(c->variant == 0 ? P * 576 * es : 0);
+  w.off_mh = take(c->variant != 1 ? P * 256 * es : 0);
+  w.off_mask = take(c->variant != 1 ? P * 576 * es : 0);
   w.off_flow = take(P * 2 * sizeof(float));
+  w.n_pad = (int)align_up((size_t)c->H * c->W, 64);
+  w.off_vbuf = take(c->variant == 2 ? P * 128 * es : 0);
+  w.off_vT = take(c->variant == 2 ? (size_t)c->B * 128 * w.n_pad * es : 0);
   w.total = off;
   return w;
 }
 
 static int check_cfg(const pfb_raft_cfg* c) {
   PFB_CHECK_ARG(c, "raft: null cfg");
-  PFB_CHECK_ARG(c->variant == 0 || c->variant == 1, "raft: variant=%d", c->variant);
+  PFB_CHECK_ARG(c->variant >= 0 && c->variant <= 2, "raft: variant=%d", c->variant);
   PFB_CHECK_ARG(dtype_ok(c->dtype), "raft: bad dtype");
   PFB_CHECK_ARG(c->B > 0 && c->H > 0 && c->W > 0, "raft: bad grid %dx%dx%d", c->B, c->H, c->W);
   PFB_CHECK_ARG(c->corr_levels >= 1 && c->corr_levels <= PFB_MAX_LEVELS && c->corr_radius >= 0 && c->corr_radius <= 15,
@@ -61,7 +68,7 @@ static int check_cfg(const pfb_raft_cfg* c) {
   PFB_CHECK_ARG((c->H >> (c->corr_levels - 1)) >= 1 && (c->W >> (c->corr_levels - 1)) >= 1,
                 "raft: %dx%d grid too small for %d levels", c->H, c->W, c->corr_levels);
   PFB_CHECK_ARG(c->hidden_dim > 0 && c->context_dim > 0 && c->iters >= 0, "raft: bad dims");
-  if (c->variant == 0) PFB_CHECK_ARG(c->hidden_dim == 128 && c->context_dim == 128, "raft: BasicUpdateBlock expects hidden=context=128");
+  if (c->variant != 1) PFB_CHECK_ARG(c->hidden_dim == 128 && c->context_dim == 128, "raft/gma: the update block expects hidden=context=128");
   else PFB_CHECK_ARG(c->hidden_dim == 96 && c->context_dim == 64, "raft_small: SmallUpdateBlock expects hidden=96 context=64");
   return PFB_OK;
 }
@@ -135,7 +142,7 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
   float* flow = reinterpret_cast<float*>(x.at(ws.off_flow));
 
   // ---- motion encoder (update.py:76-112) ----
-  if (c->variant == 0) {
+  if (c->variant != 1) {
     void* cor1 = x.at(ws.off_cor1);
     PFB_TRY(run_conv(x, PFB_L_CONVC1, {src_of(corr, ws.planes, corr_stride)}, PFB_EPI_RELU, cor1, ws.c_cor1, 0));
     PFB_TRY(run_conv(x, PFB_L_CONVC2, {src_of(cor1, ws.c_cor1, ws.c_cor1)}, PFB_EPI_RELU, corflo, ws.c_corflo, 0));
@@ -146,8 +153,38 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
   PFB_TRY(run_conv(x, PFB_L_CONVF2, {src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU, corflo, ws.c_corflo, ws.c_cor2));
   PFB_TRY(run_conv(x, PFB_L_CONV, {src_of(corflo, ws.c_corflo, ws.c_corflo)}, PFB_EPI_RELU_APPEND_FLOW, motion, ws.c_motion, 0));
 
-  // ---- GRU (update.py:24-32 ConvGRU, :58-73 SepConvGRU); x = [inp, motion] ----
-  const int halves = (c->variant == 0) ? 2 : 1;
+  // ---- gma: motion_global = motion + gamma * (attention @ to_v(motion))   gma_utils.py:101-113, gma/update.py:149 ----
+  if (c->variant == 2) {
+    PFB_CHECK_ARG(x.b->attention, "gma: null attention");
+    const int N = c->H * c->W;
+    const size_t es = dtype_size(c->dtype);
+    char* vbuf = reinterpret_cast<char*>(x.at(ws.off_vbuf));
+    char* vT = reinterpret_cast<char*>(x.at(ws.off_vT));
+    PFB_TRY(run_conv(x, PFB_L_AGG_V, {src_of(motion, 128, ws.c_motion)}, PFB_EPI_LINEAR, vbuf, 128, 0));
+    const bool tensor_path = c->dtype != PFB_F32 && c->impl != 1 && (N % 8) == 0;
+    if (tensor_path) PFB_TRY(pfb_transpose_pm(vbuf, vT, c->B, N, 128, ws.n_pad, c->dtype, (pfb_stream)x.s));
+    for (int b = 0; b < c->B; ++b) {
+      // one "1x1 convolution" per sample: pixels = queries, input channels = the N attention columns,
+      // weights = this sample's v (SIMT layout [N][128]) / v^T (K-major [128][n_pad])
+      pfb_conv_params p{};
+      p.src[0] = src_of(reinterpret_cast<const char*>(x.b->attention) + (size_t)b * N * N * es, N, N);
+      p.nsrc = 1;
+      p.B = 1; p.H = c->H; p.W = c->W; p.KH = 1; p.KW = 1;
+      p.Cout = 128; p.Cout_pad = 128;
+      p.weight = vbuf + (size_t)b * N * 128 * es;
+      p.bias = nullptr;
+      p.epilogue = PFB_EPI_AXPY; p.scale = x.b->agg_gamma;
+      char* mrow = reinterpret_cast<char*>(motion) + (size_t)b * N * ws.c_motion * es;
+      p.out = mrow; p.out_stride = ws.c_motion; p.out_offset = 128;
+      p.aux_h = mrow; p.hidden = ws.c_motion;
+      p.dtype = c->dtype; p.impl = c->impl;
+      if (tensor_path) { p.weight_k = vT + (size_t)b * 128 * ws.n_pad * es; p.Cin_pad = ws.n_pad; p.Cout_pad_k = 128; }
+      PFB_TRY(pfb_conv2d(&p, (pfb_stream)x.s));
+    }
+  }
+
+  // ---- GRU (update.py:24-32 ConvGRU, :58-73 SepConvGRU); x = [inp, motion (, motion_global)] ----
+  const int halves = (c->variant != 1) ? 2 : 1;
   for (int h = 0; h < halves; ++h) {
     const int lzr = h == 0 ? PFB_L_GRU_ZR1 : PFB_L_GRU_ZR2, lq = h == 0 ? PFB_L_GRU_Q1 : PFB_L_GRU_Q2;
     PFB_TRY(run_conv(x, lzr, {src_of(x.b->net, hd, hd), src_of(x.b->inp, cd, cd), src_of(motion, ws.c_motion, ws.c_motion)},
@@ -159,7 +196,7 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
   // ---- heads (update.py:6-14, :138-152) ----
   PFB_TRY(run_conv(x, PFB_L_FLOW1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, fh, ws.c_fh, 0));
   PFB_TRY(run_conv(x, PFB_L_FLOW2, {src_of(fh, ws.c_fh, ws.c_fh)}, PFB_EPI_FLOW, flow, 2, 0));
-  if (mask_out && c->variant == 0) {
+  if (mask_out && c->variant != 1) {
     void* mh = x.at(ws.off_mh);
     PFB_TRY(run_conv(x, PFB_L_MASK1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, mh, 256, 0));
     PFB_TRY(run_conv(x, PFB_L_MASK2, {src_of(mh, 256, 256)}, PFB_EPI_LINEAR, mask_out, 576, 0, 0.25f));
@@ -208,12 +245,12 @@ extern "C" PFB_API int pfb_raft_refine(const pfb_raft_cfg* cfg, const pfb_raft_w
   PFB_CHECK_ARG(buf->flow_up, "raft_refine: null flow_up");
   PFB_CHECK_ARG(cfg->variant == 1 || cfg->iters >= 1, "raft_refine: the convex upsample needs at least one iteration (mask)");
   PFB_TRY(launch_flow_from_coords(buf->coords, reinterpret_cast<float*>(x.at(x.ws.off_flow)), cfg->B, cfg->H, cfg->W, x.s));
-  void* mask = cfg->variant == 0 ? x.at(x.ws.off_mask) : nullptr;
+  void* mask = cfg->variant != 1 ? x.at(x.ws.off_mask) : nullptr;
   for (int it = 0; it < cfg->iters; ++it) {
     PFB_TRY(lookup(x));
     PFB_TRY(update_iter(x, nullptr, it == cfg->iters - 1 ? mask : nullptr));
   }
-  if (cfg->variant == 0)
+  if (cfg->variant != 1)
     return pfb_convex_upsample(buf->coords, mask, buf->flow_up, buf->flow_small, cfg->B, cfg->H, cfg->W, cfg->out_h,
                                cfg->out_w, cfg->pad_top, cfg->pad_left, cfg->dtype, stream);
   return pfb_upflow8(buf->coords, buf->flow_up, buf->flow_small, cfg->B, cfg->H, cfg->W, cfg->out_h, cfg->out_w,

@@ -21,7 +21,8 @@ class RaftEngine:
     ``load_state_dict`` -- model_benchmark.py:274-279, infer.py:148-152)."""
 
     def __init__(self, update_block: torch.nn.Module, variant: int, hidden_dim: int, context_dim: int,
-                 corr_levels: int, corr_radius: int, dtype: torch.dtype, device: torch.device, impl: int = 0):
+                 corr_levels: int, corr_radius: int, dtype: torch.dtype, device: torch.device, impl: int = 0,
+                 attention_module: Optional[torch.nn.Module] = None):
         self.variant, self.hidden_dim, self.context_dim = variant, hidden_dim, context_dim
         self.corr_levels, self.corr_radius = corr_levels, corr_radius
         self.dtype, self.device, self.impl = dtype, device, impl
@@ -35,12 +36,14 @@ class RaftEngine:
 
         layers: Dict[int, ops.PackedConv] = {}
         layers[_lib.L_CONVF1] = P(None, enc.convf1)  # 7x7 on the 2-channel fp32 flow: dedicated kernel
-        if variant == 0:
+        if variant in (0, 2):
             layers[_lib.L_CONVC1] = P([planes], enc.convc1)
             layers[_lib.L_CONVC2] = P([256], enc.convc2)
             layers[_lib.L_CONVF2] = P([128], enc.convf2)
             layers[_lib.L_CONV] = P([256], enc.conv)  # cat[cor(192), flo(64)] lives in one 256-channel buffer
-            gsrc = [hd, cd, 128]  # cat[h or r*h, inp, motion] -- three tensor maps, no concat copy
+            # cat[h or r*h, inp, motion (, motion_global)] -- three tensor maps, no concat copy (gma keeps
+            # motion | motion_global in one 256-channel buffer)
+            gsrc = [hd, cd, 256 if variant == 2 else 128]
             layers[_lib.L_GRU_ZR1] = P(gsrc, gru.convz1, gru.convr1)  # z | r share the input: one GEMM, N = 2*hidden
             layers[_lib.L_GRU_Q1] = P(gsrc, gru.convq1)
             layers[_lib.L_GRU_ZR2] = P(gsrc, gru.convz2, gru.convr2)
@@ -57,6 +60,21 @@ class RaftEngine:
             layers[_lib.L_GRU_Q1] = P(None, gru.convq)
             layers[_lib.L_FLOW1] = P(None, fh.conv1)
             layers[_lib.L_FLOW2] = P(None, fh.conv2)
+        self.agg_gamma = 0.0
+        self.att_q = self.att_k = None
+        if variant == 2:
+            agg = ub.aggregator
+            layers[_lib.L_AGG_V] = P([128], agg.to_v)
+            self.agg_gamma = float(agg.gamma.detach().float().cpu().item())
+
+            class _Half:  # q / k halves of Attention.to_qk as separate 1x1 layers (contiguous outputs for the GEMM)
+                def __init__(self, w):
+                    self.weight, self.bias = w, None
+
+            wqk = attention_module.to_qk.weight
+            c = wqk.shape[0] // 2
+            self.att_q = ops.PackedConv([_Half(wqk[:c])], dtype, device, src_channels=[wqk.shape[1]])
+            self.att_k = ops.PackedConv([_Half(wqk[c:])], dtype, device, src_channels=[wqk.shape[1]])
         self.layers = layers
         self.weights = _lib.RaftWeights()
         for k, v in layers.items():
@@ -87,7 +105,7 @@ class RaftEngine:
         return ws
 
     def refine(self, pyramid: Sequence[torch.Tensor], net: torch.Tensor, inp: torch.Tensor, coords: torch.Tensor,
-               iters: int, out_hw, pad, fmap1: Optional[torch.Tensor] = None):
+               iters: int, out_hw, pad, fmap1: Optional[torch.Tensor] = None, attention: Optional[torch.Tensor] = None):
         """Runs the loop in place on (net, coords); returns (flow_up fp32 [B,2,oh,ow], flow_small fp32 [B,2,H,W])."""
         B, H, W, _ = net.shape
         alt = fmap1 is not None
@@ -98,7 +116,7 @@ class RaftEngine:
         pyr = ptr_array(pyramid)
         buf = _lib.RaftBuffers(C.cast(pyr, C.POINTER(C.c_void_p)), fmap1.data_ptr() if alt else None, net.data_ptr(),
                                inp.data_ptr(), coords.data_ptr(), flow_up.data_ptr(), flow_small.data_ptr(),
-                               ws.data_ptr(), ws.numel())
+                               ws.data_ptr(), ws.numel(), attention.data_ptr() if attention is not None else None, self.agg_gamma)
         with torch.cuda.device(self.device):
             check(load().pfb_raft_refine(C.byref(cfg), C.byref(self.weights), C.byref(buf), stream_ptr(self.device)), "raft_refine")
         return flow_up, flow_small
@@ -112,7 +130,7 @@ class RaftEngine:
         mask = torch.empty((B, H, W, 576), dtype=self.dtype, device=self.device) if (want_mask and self.variant == 0) else None
         pyr = ptr_array(pyramid) if pyramid is not None else None
         buf = _lib.RaftBuffers(C.cast(pyr, C.POINTER(C.c_void_p)) if pyr is not None else None, None, net.data_ptr(), inp.data_ptr(),
-                               coords.data_ptr(), None, None, ws.data_ptr(), ws.numel())
+                               coords.data_ptr(), None, None, ws.data_ptr(), ws.numel(), None, 0.0)
         with torch.cuda.device(self.device):
             check(load().pfb_raft_update_iter(C.byref(cfg), C.byref(self.weights), C.byref(buf),
                                               corr.data_ptr() if corr is not None else None,

@@ -76,11 +76,23 @@ class RAFT(BaseModel):
         eng = self._engine
         if (eng is None or eng.dtype != dtype or eng.device != device or eng.impl != self.kernel_impl
                 or eng.corr_levels != self.corr_levels or eng.corr_radius != self.corr_radius
-                or eng.signature != RaftEngine.param_signature(self.update_block)):
+                or eng.signature != RaftEngine.param_signature(self.update_block)
+                or getattr(eng, "extra_signature", None) != self._extra_signature()):
             eng = RaftEngine(self.update_block, self._variant, self.hidden_dim, self.context_dim, self.corr_levels,
-                             self.corr_radius, dtype, device, impl=self.kernel_impl)
+                             self.corr_radius, dtype, device, impl=self.kernel_impl, **self._extra_engine_args())
+            eng.extra_signature = self._extra_signature()
             self._engine = eng
         return eng
+
+    def _extra_engine_args(self) -> Dict:
+        return {}
+
+    def _extra_signature(self):
+        mod = self._extra_engine_args().get("attention_module")
+        return None if mod is None else tuple((p.data_ptr(), p._version) for p in mod.parameters())
+
+    def _attention(self, inp: torch.Tensor, eng):
+        return None
 
     def _encode(self, frames: torch.Tensor, B: int):
         """frames: pixel-major [2B,Hp,Wp,3] (frame 1 of every pair first).  Both frames go through fnet as one
@@ -130,7 +142,9 @@ class RAFT(BaseModel):
 
             orig_h, orig_w = inputs["images"].shape[-2:]
             pad_top, pad_left = resizer.pad_top_left
-            flow_up, flow_small = eng.refine(pyramid, net, inp, coords, self.iters, (orig_h, orig_w), (pad_top, pad_left), fmap1=f1)
+            attention = self._attention(inp, eng)  # gma only (gma.py:181)
+            flow_up, flow_small = eng.refine(pyramid, net, inp, coords, self.iters, (orig_h, orig_w), (pad_top, pad_left), fmap1=f1,
+                                             attention=attention)
             flow_up = self.postprocess_predictions(flow_up, resizer, is_flow=True)  # no-op: written un-padded
             out_dtype = inputs["images"].dtype
             return {"flows": flow_up.to(out_dtype)[:, None], "flow_small": flow_small.to(out_dtype),

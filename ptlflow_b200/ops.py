@@ -217,6 +217,15 @@ def upflow8(coords: torch.Tensor, out_hw=None, pad=(0, 0)):
     return up, small
 
 
+def softmax_rows(x: torch.Tensor) -> torch.Tensor:
+    """In-place softmax over the last axis of a 2-D tensor (GMA attention, gma_utils.py:74)."""
+    require_cuda(x, "x")
+    rows, cols = x.shape
+    with torch.cuda.device(x.device):
+        check(load().pfb_softmax_rows(x.data_ptr(), rows, cols, dtype_code(x.dtype), stream_ptr(x.device)), "softmax_rows")
+    return x
+
+
 def init_coords(B: int, H: int, W: int, device, flow_init: Optional[torch.Tensor] = None) -> torch.Tensor:
     coords = torch.empty((B, H, W, 2), dtype=torch.float32, device=device)
     fi = None

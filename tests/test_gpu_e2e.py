@@ -60,7 +60,7 @@ def test_fp32_matches_reference_vectors(name):
     assert err_small < 1e-3
 
 
-@pytest.mark.parametrize("name", ["e2e_raft_noise", "e2e_raft_smooth_b2", "e2e_raft_altcorr"])
+@pytest.mark.parametrize("name", ["e2e_raft_noise", "e2e_raft_smooth_b2", "e2e_raft_altcorr", "e2e_gma"])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_half_against_fp32_reference(name, dtype):
     """Storage in f16/bf16, coordinates / accumulators / gates in fp32.  The bound asserted here is

@@ -326,3 +326,29 @@ def test_encoders_vs_oracle_fp32(variant):
     cref = O.encoder(frames[:2], sd, "cnet.", "none" if small else "batch", small)
     assert (f.permute(0, 3, 1, 2).cpu() - fref).abs().max().item() < 2e-4
     assert (c.permute(0, 3, 1, 2).cpu() - cref).abs().max().item() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------
+# a13: GMA attention + aggregate (operator level, against the oracle)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 2e-2)])
+@pytest.mark.parametrize("h,w", [(8, 16), (9, 13)])  # N = 128 (tensor path in f16) and N = 117 (SIMT fallback)
+def test_gma_attention_and_aggregate_vs_oracle(dtype, tol, h, w):
+    import ptlflow_b200 as pb
+    from ptlflow_b200 import _lib
+    from ptlflow_b200.engine import RaftEngine
+
+    ops = _ops()
+    b = 2
+    sd = synth.synth_state_dict({k: v for k, v in O.state_dict_shapes("gma").items() if k.split(".")[0] in ("update_block", "att")}, 5)
+    model = pb.get_model("gma")
+    model.update_block.load_state_dict({k[len("update_block."):]: v for k, v in sd.items() if k.startswith("update_block.")})
+    model.att.load_state_dict({k[len("att."):]: v for k, v in sd.items() if k.startswith("att.")})
+    model.update_block.to(DEV), model.att.to(DEV)
+    eng = RaftEngine(model.update_block, 2, 128, 128, 4, 4, dtype, torch.device(DEV), attention_module=model.att)
+    inp = torch.relu(torch.from_numpy(synth.synth_normal("gma/inp", (b, 128, h, w), 6)))
+    attn_ref = O.gma_attention(inp.to(dtype).float(), {k: v.to(dtype).float() for k, v in sd.items()})
+    attn = model._attention(_nhwc(inp, dtype), eng)
+    assert attn.shape == (b * h * w, h * w)
+    assert (attn.float().cpu().view(b, h * w, h * w) - attn_ref).abs().max().item() < tol
+    assert (attn.float().sum(-1) - 1).abs().max().item() < (1e-5 if dtype == torch.float32 else 5e-3)

@@ -28,7 +28,7 @@ def test_registry_and_get_model():
     assert m2.iters == 4 and m2.hidden_dim == 96
 
 
-@pytest.mark.parametrize("variant", ["raft", "raft_small"])
+@pytest.mark.parametrize("variant", ["raft", "raft_small", "gma"])
 def test_state_dict_keys_equal_reference(variant):
     import ptlflow_b200 as pb
 
