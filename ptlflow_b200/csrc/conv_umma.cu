@@ -110,7 +110,10 @@ __device__ __forceinline__ void load32(const T* src, float (&v)[32]) {
   }
 }
 
-template <typename T>
+// CG = 1: one CTA per MMA (M = 128).  CG = 2: CTA pairs (cta_group::2, M = 256): the pair shares every weight
+// tile -- each CTA stages only half of its rows and the tensor cores of both SMs read both halves -- which
+// halves the shared-memory traffic per MMA, the limiter of the single-CTA version.
+template <typename T, int CG>
 __global__ void __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW, const ConvUmmaArgs a) {
@@ -124,6 +127,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   int chunks = 0;
   for (int s = 0; s < a.nsrc; ++s) chunks += a.src_chunks[s];
   const int tiles_m = a.tiles_x * a.tiles_y * a.B;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;  // 0 = MMA leader
+  const int group0 = blockIdx.x / CG, group_stride = gridDim.x / CG;
+  const int pairs_m = (tiles_m + CG - 1) / CG;              // work items per N tile (an item = CG adjacent M tiles)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.a_stages; ++s) {
@@ -136,24 +142,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bars->acc_full[t], 1);
-      mbar_init(&bars->acc_empty[t], 8);  // one arrival per epilogue warp
+      mbar_init(&bars->acc_empty[t], 8 * CG);  // one arrival per epilogue warp (of both CTAs in pair mode)
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == 5) {
+    if (CG == 2) tmem_alloc_2cta<512>(&bars->tmem_base);
+    else tmem_alloc<512>(&bars->tmem_base);
+  }
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tm0);
     prefetch_tmap(&tmW);
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  // work item w -> (n tile, image, tile row, tile col); n-tile major so concurrent CTAs share the weight tile in L2
-  auto decode = [&](int w, int& n0, int& b, int& y0, int& x0) {
-    const int nt = w / tiles_m;
-    int m = w - nt * tiles_m;
+  // work item j -> (n tile, image, tile row, tile col) of THIS CTA; n-tile major so concurrent CTAs share the weight
+  // tile in L2.  In pair mode the two CTAs take adjacent M tiles; a missing partner tile decodes to b == B
+  // (all its TMA loads fall outside the tensor and are zero-filled, its stores are masked).
+  auto decode = [&](int j, int& n0, int& b, int& y0, int& x0) {
+    const int nt = j / pairs_m;
+    int m = (j - nt * pairs_m) * CG + rank;
+    if (m >= tiles_m) m = tiles_m;  // -> b == B
     const int px = m % a.tiles_x;
     m /= a.tiles_x;
     const int py = m % a.tiles_y;
@@ -167,11 +180,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // ================= TMA producer =================
     if (lane == 0) {
       const int ph2 = a.KH >> 1, pw2 = a.KW >> 1;
-      const uint32_t btx = a.NT * 128;
+      const uint32_t btx = a.NT * 128;  // bytes of the whole weight tile (both halves in pair mode)
+      const int brow = rank * (a.NT / CG);  // this CTA stages rows [brow, brow + NT / CG) of the weight tile
       // ring positions advance incrementally (stage index + phase bit): no integer division on the issue path
       int sta = 0, stb = 0;
       uint32_t pha = 0, phb = 0;
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+      for (int w = group0; w < a.n_work; w += group_stride) {
         int n0, b, y0, x0;
         decode(w, n0, b, y0, x0);
         int kidx = 0;
@@ -183,14 +197,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
               for (int kx = 0; kx < a.KW; ++kx) {
                 if (kx == 0 || !a.halo) {  // activation patch: once per (chunk, ky) in halo mode, else once per tap
                   mbar_wait(&bars->a_empty[sta], pha ^ 1);
-                  mbar_arrive_expect_tx(&bars->a_full[sta], a.a_tx_bytes);
-                  tma_load_4d(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
-                              x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
+                  // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
+                  if (rank == 0) mbar_arrive_expect_tx(&bars->a_full[sta], a.a_tx_bytes * CG);
+                  if (CG == 2)
+                    tma_load_4d_2cta(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
+                                     x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
+                  else
+                    tma_load_4d(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
+                                x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
                   if (++sta == a.a_stages) { sta = 0; pha ^= 1; }
                 }
                 mbar_wait(&bars->b_empty[stb], phb ^ 1);
-                mbar_arrive_expect_tx(&bars->b_full[stb], btx);
-                tma_load_2d(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0);
+                if (rank == 0) mbar_arrive_expect_tx(&bars->b_full[stb], btx);
+                if (CG == 2) tma_load_2d_2cta(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0 + brow);
+                else tma_load_2d(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0);
                 wrow += a.Cout_pad_k;
                 if (++stb == a.b_stages) { stb = 0; phb ^= 1; }
               }
@@ -204,8 +224,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // One thread issues everything, so its instruction count per tap IS the pacing of the tensor pipe when the
     // tile is small (ncu: ~130 SASS instructions/tap at ~8 clk each paced the first version).  Everything that can
     // be precomputed is: 32-bit shared addresses of barriers and slots, descriptor words updated by adds only.
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, a.NT, a.ab_fmt);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_f16(128 * CG, a.NT, a.ab_fmt);
       // descriptor = {lo: (addr >> 4) | LBO(1) << 16, hi: SBO(1024 >> 4) | version 1 << 14 | SWIZZLE_128B 2 << 29}
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_slot16 = (uint32_t)a.a_slot_bytes >> 4, b_slot16 = (uint32_t)a.b_slot_bytes >> 4;
@@ -218,7 +238,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       int sa = 0, sb = 0, i = 0;
       uint32_t pha = 0, phb = 0;
       uint32_t a_lo = a_lo0, b_lo = b_lo0;
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++i) {
+      for (int w = group0; w < a.n_work; w += group_stride, ++i) {
         const int t = i & 1;
         mbar_wait(&bars->acc_empty[t], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -232,18 +252,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             const uint32_t al = a_lo + 8 * kx;  // halo: tap kx starts kx pixel rows (128 B) into the patch
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              umma_f16_lohi(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, acc);
+              if (CG == 2) umma_f16_lohi_2cta(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, acc);
+              else umma_f16_lohi(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, acc);
               acc = 1;
             }
-            umma_commit_addr(bar_b_empty + 8 * sb);
+            if (CG == 2) umma_commit_addr_2cta(bar_b_empty + 8 * sb);
+            else umma_commit_addr(bar_b_empty + 8 * sb);
             b_lo += b_slot16;
             if (++sb == a.b_stages) { sb = 0; phb ^= 1; b_lo = b_lo0; }
           }
-          umma_commit_addr(bar_a_empty + 8 * sa);
+          if (CG == 2) umma_commit_addr_2cta(bar_a_empty + 8 * sa);
+          else umma_commit_addr(bar_a_empty + 8 * sa);
           a_lo += a_slot16;
           if (++sa == a.a_stages) { sa = 0; pha ^= 1; a_lo = a_lo0; }
         }
-        umma_commit(&bars->acc_full[t]);
+        if (CG == 2) umma_commit_addr_2cta(smem_u32(&bars->acc_full[t]));
+        else umma_commit(&bars->acc_full[t]);
       }
     }
   } else {
@@ -254,12 +278,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     const int row = quarter * 32 + lane;
     const int hd = a.hidden;
     int i = 0;
-    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++i) {
+    for (int w = group0; w < a.n_work; w += group_stride, ++i) {
       int n0, b, y0, x0;
       decode(w, n0, b, y0, x0);
       const int t = i & 1, tuse = i >> 1;
       const int y = y0 + (row >> a.tw_shift), x = x0 + (row & (a.TW - 1));
-      const bool ok = (y < a.H) && (x < a.W);
+      const bool ok = (y < a.H) && (x < a.W) && (b < a.B);
       const size_t p = ((size_t)b * a.H + (ok ? y : 0)) * a.W + (ok ? x : 0);
       mbar_wait(&bars->acc_full[t], tuse & 1);
       tc_fence_after();
@@ -376,12 +400,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[t]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&bars->acc_empty[t]);  // the leader's MMA thread owns the accumulator hand-off
+        else mbar_arrive(&bars->acc_empty[t]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem_base);
+  if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 5) {
+    if (CG == 2) tmem_dealloc_2cta<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,16 +453,27 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
   return true;
 }
 
-template <typename T>
-static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const ConvUmmaArgs& a, dim3 grid, size_t smem,
+template <typename T, int CG>
+static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const ConvUmmaArgs& a, int grid, size_t smem,
                             cudaStream_t s) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_umma_kernel<T><<<grid, 320, smem, s>>>(tms[0], tms[1], tms[2], tmW, a);
-  PFB_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PFB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, CG>, tms[0], tms[1], tms[2], tmW, a));
   return PFB_OK;
 }
 
@@ -450,6 +492,7 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   CUtensorMap tms[3];
   pick_tile(p->H, p->W, a.TW, a.TH);
   static const int env_halo = getenv("PFB_CONV_HALO") ? atoi(getenv("PFB_CONV_HALO")) : 1;
+  static const int env_cg = getenv("PFB_CONV_CTA_PAIR") ? atoi(getenv("PFB_CONV_CTA_PAIR")) : 1;
   static const int env_desc = getenv("PFB_UMMA_DESC_MODE") ? atoi(getenv("PFB_UMMA_DESC_MODE")) : 0;
   a.halo = (env_halo && a.TH == 1 && p->KW > 1) ? 1 : 0;
   a.desc_base_offset_mode = env_desc;
@@ -471,23 +514,25 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   for (int i = p->nsrc; i < 3; ++i) tms[i] = tms[0];
   a.n_tiles = ceil_div(p->Cout_pad_k, 256);
   a.NT = p->Cout_pad_k / a.n_tiles;
+  // CTA pairs split the weight tile in two: needs an even row count per half (UMMA N % 16) -> NT % 32, always true here
+  const int CG = (env_cg && (sm_count() % 2) == 0) ? 2 : 1;
   a.acc_stride = a.NT > 128 ? 256 : 128;
   CUtensorMap tmW;
   {
     uint64_t dims[2] = {(uint64_t)p->Cin_pad, (uint64_t)p->KH * p->KW * p->Cout_pad_k};
     uint64_t str[1] = {(uint64_t)p->Cin_pad * 2};
-    uint32_t box[2] = {64, (uint32_t)a.NT};
+    uint32_t box[2] = {64, (uint32_t)(a.NT / CG)};
     int rc = make_tensor_map(&tmW, p->weight_k, p->dtype, 2, dims, str, box);
     if (rc) return rc;
   }
   a.B = p->B; a.H = p->H; a.W = p->W; a.KH = p->KH; a.KW = p->KW;
   a.tiles_x = ceil_div(p->W, a.TW);
   a.tiles_y = ceil_div(p->H, a.TH);
-  a.n_work = a.tiles_x * a.tiles_y * p->B * a.n_tiles;
+  a.n_work = ceil_div(a.tiles_x * a.tiles_y * p->B, CG) * a.n_tiles;  // items of CG adjacent M tiles
   a.Cout = p->Cout; a.Cout_pad_k = p->Cout_pad_k;
   a.a_tx_bytes = patch_w * a.TH * 128;
   a.a_slot_bytes = (int)align_up((size_t)a.a_tx_bytes, 1024);
-  a.b_slot_bytes = a.NT * 128;
+  a.b_slot_bytes = (a.NT / CG) * 128;
   {
     // split ~212 KB between the rings: in halo mode one A patch feeds KW weight tiles, so B gets the depth
     const int budget = 212 * 1024;
@@ -503,10 +548,16 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.aux_h = p->aux_h; a.aux_z = p->aux_z; a.hidden = p->hidden; a.flow = p->flow;
   a.ab_fmt = p->dtype == PFB_F16 ? 0 : 1;
   const size_t smem = (size_t)a.a_stages * a.a_slot_bytes + (size_t)a.b_stages * a.b_slot_bytes + sizeof(ConvBars) + 1024;
-  dim3 grid(a.n_work < sm_count() ? a.n_work : sm_count());
+  int groups = sm_count() / CG;
+  if (groups > a.n_work) groups = a.n_work;
+  const int grid = groups * CG;
   ProfScope prof(KC_CONV, s);
-  if (p->dtype == PFB_F16) return launch_conv_umma<__half>(tms, tmW, a, grid, smem, s);
-  return launch_conv_umma<__nv_bfloat16>(tms, tmW, a, grid, smem, s);
+  if (CG == 2) {
+    if (p->dtype == PFB_F16) return launch_conv_umma<__half, 2>(tms, tmW, a, grid, smem, s);
+    return launch_conv_umma<__nv_bfloat16, 2>(tms, tmW, a, grid, smem, s);
+  }
+  if (p->dtype == PFB_F16) return launch_conv_umma<__half, 1>(tms, tmW, a, grid, smem, s);
+  return launch_conv_umma<__nv_bfloat16, 1>(tms, tmW, a, grid, smem, s);
 }
 
 }  // namespace pfb
