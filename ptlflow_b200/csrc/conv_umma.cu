@@ -177,8 +177,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   };
 
   if (warp == 4) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
+    {
       const int ph2 = a.KH >> 1, pw2 = a.KW >> 1;
       const uint32_t btx = a.NT * 128;  // bytes of the whole weight tile (both halves in pair mode)
       const int brow = rank * (a.NT / CG);  // this CTA stages rows [brow, brow + NT / CG) of the weight tile
@@ -197,20 +197,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
               for (int kx = 0; kx < a.KW; ++kx) {
                 if (kx == 0 || !a.halo) {  // activation patch: once per (chunk, ky) in halo mode, else once per tap
                   mbar_wait(&bars->a_empty[sta], pha ^ 1);
-                  // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
-                  if (rank == 0) mbar_arrive_expect_tx(&bars->a_full[sta], a.a_tx_bytes * CG);
-                  if (CG == 2)
-                    tma_load_4d_2cta(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
-                                     x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
-                  else
-                    tma_load_4d(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
-                                x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
+                  if (elect_one()) {
+                    // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
+                    if (rank == 0) mbar_arrive_expect_tx(&bars->a_full[sta], a.a_tx_bytes * CG);
+                    if (CG == 2)
+                      tma_load_4d_2cta(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
+                                       x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
+                    else
+                      tma_load_4d(smemA + sta * a.a_slot_bytes, tm, &bars->a_full[sta], a.src_coff[s] + c * 64,
+                                  x0 - pw2 + (a.halo ? 0 : kx), y0 + ky - ph2, b);
+                  }
+                  __syncwarp();
                   if (++sta == a.a_stages) { sta = 0; pha ^= 1; }
                 }
                 mbar_wait(&bars->b_empty[stb], phb ^ 1);
-                if (rank == 0) mbar_arrive_expect_tx(&bars->b_full[stb], btx);
-                if (CG == 2) tma_load_2d_2cta(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0 + brow);
-                else tma_load_2d(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0);
+                if (elect_one()) {
+                  if (rank == 0) mbar_arrive_expect_tx(&bars->b_full[stb], btx);
+                  if (CG == 2) tma_load_2d_2cta(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0 + brow);
+                  else tma_load_2d(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0);
+                }
+                __syncwarp();
                 wrow += a.Cout_pad_k;
                 if (++stb == a.b_stages) { stb = 0; phb ^= 1; }
               }
@@ -224,7 +230,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     // One thread issues everything, so its instruction count per tap IS the pacing of the tensor pipe when the
     // tile is small (ncu: ~130 SASS instructions/tap at ~8 clk each paced the first version).  Everything that can
     // be precomputed is: 32-bit shared addresses of barriers and slots, descriptor words updated by adds only.
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp walks the loop (warp-uniform control flow, all lanes poll the barriers) and one elected lane
+    // issues the MMAs / commits: under a divergent `lane == 0` branch ptxas wraps every tcgen05 instruction in its
+    // own ELECT / vote / branch sequence, which showed up as most of the issue thread's time in the ncu source view.
+    if (rank == 0) {
       const uint32_t idesc = make_idesc_f16(128 * CG, a.NT, a.ab_fmt);
       // descriptor = {lo: (addr >> 4) | LBO(1) << 16, hi: SBO(1024 >> 4) | version 1 << 14 | SWIZZLE_128B 2 << 29}
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -250,24 +259,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             mbar_wait_addr(bar_b_full + 8 * sb, phb);
             tc_fence_after();
             const uint32_t al = a_lo + 8 * kx;  // halo: tap kx starts kx pixel rows (128 B) into the patch
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              if (CG == 2) umma_f16_lohi_2cta(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, acc);
-              else umma_f16_lohi(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, acc);
-              acc = 1;
+              for (int kk = 0; kk < 4; ++kk) {
+                if (CG == 2) umma_f16_lohi_2cta(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, kk == 0 ? acc : 1u);
+                else umma_f16_lohi(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, kk == 0 ? acc : 1u);
+              }
+              if (CG == 2) umma_commit_addr_2cta(bar_b_empty + 8 * sb);
+              else umma_commit_addr(bar_b_empty + 8 * sb);
+              if (kx == kw_halo - 1) {
+                if (CG == 2) umma_commit_addr_2cta(bar_a_empty + 8 * sa);
+                else umma_commit_addr(bar_a_empty + 8 * sa);
+              }
             }
-            if (CG == 2) umma_commit_addr_2cta(bar_b_empty + 8 * sb);
-            else umma_commit_addr(bar_b_empty + 8 * sb);
+            __syncwarp();
+            acc = 1;
             b_lo += b_slot16;
             if (++sb == a.b_stages) { sb = 0; phb ^= 1; b_lo = b_lo0; }
           }
-          if (CG == 2) umma_commit_addr_2cta(bar_a_empty + 8 * sa);
-          else umma_commit_addr(bar_a_empty + 8 * sa);
           a_lo += a_slot16;
           if (++sa == a.a_stages) { sa = 0; pha ^= 1; a_lo = a_lo0; }
         }
-        if (CG == 2) umma_commit_addr_2cta(smem_u32(&bars->acc_full[t]));
-        else umma_commit(&bars->acc_full[t]);
+        if (elect_one()) {
+          if (CG == 2) umma_commit_addr_2cta(smem_u32(&bars->acc_full[t]));
+          else umma_commit(&bars->acc_full[t]);
+        }
+        __syncwarp();
       }
     }
   } else {
