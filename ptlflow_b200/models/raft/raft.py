@@ -57,6 +57,10 @@ class RAFT(BaseModel):
         # backend knobs (not hparams): 0 auto, 1 SIMT fp32-accumulate kernels, 2 force tcgen05
         self.kernel_impl = 0
         self.strict_fp32 = True  # fp32 models: keep cuDNN off TF32 so the 1e-3 parity gate holds
+        # images per encoder pass (0 = whole batch).  Smaller passes keep the 1/2-resolution intermediates of the
+        # norm / activation kernels inside the 126 MB L2 instead of streaming them through HBM.
+        import os as _os
+        self.encoder_chunk = int(_os.environ.get("PFB_ENCODER_CHUNK", "0"))
         self._engine: Optional[RaftEngine] = None
         self._build_networks()
 
@@ -97,13 +101,19 @@ class RAFT(BaseModel):
     def _encode(self, frames: torch.Tensor, B: int):
         """frames: pixel-major [2B,Hp,Wp,3] (frame 1 of every pair first).  Both frames go through fnet as one
         batch (instance norm is per sample, extractor.py:173-176); cnet sees frame 1 only."""
+        def run(net, x):
+            n = self.encoder_chunk
+            if n <= 0 or x.shape[0] <= n:
+                return net.forward_pm(x)
+            return torch.cat([net.forward_pm(x[i : i + n]) for i in range(0, x.shape[0], n)], dim=0)
+
         if frames.dtype == torch.float32 and self.strict_fp32:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                fmaps = self.fnet.forward_pm(frames)
-                cnet = self.cnet.forward_pm(frames[:B])
+                fmaps = run(self.fnet, frames)
+                cnet = run(self.cnet, frames[:B])
         else:
-            fmaps = self.fnet.forward_pm(frames)
-            cnet = self.cnet.forward_pm(frames[:B])
+            fmaps = run(self.fnet, frames)
+            cnet = run(self.cnet, frames[:B])
         return fmaps[:B], fmaps[B:], cnet
 
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
