@@ -105,56 +105,55 @@ __global__ void inorm_finalize_kernel(const double* __restrict__ stats, float2* 
 }
 
 // y = act(x * scale + shift)  [+ residual -> relu];  scale/shift per (sample, channel) (ss_bstride = C) or per
-// channel (ss_bstride = 0).  8 channels (16 bytes) per thread.
+// channel (ss_bstride = 0).  grid = (pixel slabs, B); a thread owns one channel octet (its 8 scale/shift pairs
+// live in registers for the whole slab) and walks pixels with 16-byte loads, four pixels in flight.
 template <typename T>
-__global__ void affine_act_kernel(const T* __restrict__ x, const float2* __restrict__ ss, const T* __restrict__ residual,
-                                  T* __restrict__ y, size_t total8, int HW, int C, int ss_bstride, int relu) {
-  const int c8n = C / 8;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total8; idx += (size_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(idx % c8n) * 8;
-    const size_t b = idx / ((size_t)HW * c8n);
-    const float2* s = ss + b * ss_bstride + c0;
-    uint4 xv = reinterpret_cast<const uint4*>(x)[idx];
-    uint4 rv = residual ? reinterpret_cast<const uint4*>(residual)[idx] : make_uint4(0u, 0u, 0u, 0u);
-    const T* xe = reinterpret_cast<const T*>(&xv);
-    const T* re = reinterpret_cast<const T*>(&rv);
-    uint4 ov;
-    T* oe = reinterpret_cast<T*>(&ov);
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]) {
+  uint4 u;
+  T* h = reinterpret_cast<T*>(&u);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float2 sc = __ldg(s + k);
-      float v = fmaf(to_f32(xe[k]), sc.x, sc.y);
-      if (relu) v = fmaxf(v, 0.f);
-      if (residual) v = fmaxf(to_f32(re[k]) + v, 0.f);
-      oe[k] = from_f32<T>(v);
-    }
-    reinterpret_cast<uint4*>(y)[idx] = ov;
-  }
+  for (int i = 0; i < 8; ++i) h[i] = from_f32<T>(f[i]);
+  *reinterpret_cast<uint4*>(p) = u;
 }
 template <>
-__global__ void affine_act_kernel<float>(const float* __restrict__ x, const float2* __restrict__ ss,
-                                         const float* __restrict__ residual, float* __restrict__ y, size_t total8, int HW, int C,
-                                         int ss_bstride, int relu) {
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x, const float2* __restrict__ ss,
+                                                         const T* __restrict__ residual, T* __restrict__ y, int HW, int C,
+                                                         int ss_bstride, int relu, int pix_per_block) {
+  const int b = blockIdx.y;
   const int c8n = C / 8;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total8; idx += (size_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(idx % c8n) * 8;
-    const size_t b = idx / ((size_t)HW * c8n);
-    const float2* s = ss + b * ss_bstride + c0;
+  const int lanes = blockDim.x / c8n;
+  const int co = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+  if (pl >= lanes) return;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float4 xv = reinterpret_cast<const float4*>(x)[2 * idx + h];
-      float4 rv = residual ? reinterpret_cast<const float4*>(residual)[2 * idx + h] : make_float4(0.f, 0.f, 0.f, 0.f);
-      float xe[4] = {xv.x, xv.y, xv.z, xv.w}, re[4] = {rv.x, rv.y, rv.z, rv.w}, oe[4];
+  for (int k = 0; k < 8; ++k) {
+    const float2 v = __ldg(ss + (size_t)b * ss_bstride + 8 * co + k);
+    sc[k] = v.x;
+    sh[k] = v.y;
+  }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, HW);
+  const size_t base = (size_t)b * HW * C + 8 * co;
+#pragma unroll 4
+  for (int p = p0 + pl; p < p1; p += lanes) {
+    const size_t off = base + (size_t)p * C;
+    float v[8], r[8];
+    load8<T>(x + off, v);
+    if (residual) load8<T>(residual + off, r);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 sc = __ldg(s + 4 * h + k);
-        float v = fmaf(xe[k], sc.x, sc.y);
-        if (relu) v = fmaxf(v, 0.f);
-        if (residual) v = fmaxf(re[k] + v, 0.f);
-        oe[k] = v;
-      }
-      reinterpret_cast<float4*>(y)[2 * idx + h] = make_float4(oe[0], oe[1], oe[2], oe[3]);
+    for (int k = 0; k < 8; ++k) {
+      float o = fmaf(v[k], sc[k], sh[k]);
+      if (relu) o = fmaxf(o, 0.f);
+      if (residual) o = fmaxf(r[k] + o, 0.f);
+      v[k] = o;
     }
+    store8<T>(y + off, v);
   }
 }
 
@@ -191,9 +190,9 @@ extern "C" PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C) {
 template <typename T>
 static int launch_affine(const void* x, const float2* ss, const void* residual, void* y, int B, int HW, int C, int bstride, int relu,
                          cudaStream_t s) {
-  const size_t total8 = (size_t)B * HW * C / 8;
-  unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total8, 256), (size_t)sm_count() * 16);
-  affine_act_kernel<T><<<blocks, 256, 0, s>>>((const T*)x, ss, (const T*)residual, (T*)y, total8, HW, C, bstride, relu);
+  const int ppb = HW >= 8192 ? 512 : (HW >= 1024 ? 128 : 32);
+  dim3 grid(ceil_div(HW, ppb), B);
+  affine_act_kernel<T><<<grid, 256, 0, s>>>((const T*)x, ss, (const T*)residual, (T*)y, HW, C, bstride, relu, ppb);
   PFB_LAUNCH_CHECK();
   return PFB_OK;
 }
@@ -226,6 +225,7 @@ extern "C" PFB_API int pfb_bias_act(const void* x, const float* bias, const void
                                     int W, int C, int relu, pfb_dtype dtype, pfb_stream stream) {
   PFB_CHECK_ARG(x && y && workspace, "bias_act: null pointer");
   PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bias_act: bad shape (C=%d must be a multiple of 8)", C);
+  PFB_CHECK_ARG(B <= 65535, "bias_act: batch too large");
   cudaStream_t s = as_stream(stream);
   float2* ss = reinterpret_cast<float2*>(workspace);
   ProfScope prof(KC_MISC, s);

@@ -61,6 +61,7 @@ class RAFT(BaseModel):
         # norm / activation kernels inside the 126 MB L2 instead of streaming them through HBM.
         import os as _os
         self.encoder_chunk = int(_os.environ.get("PFB_ENCODER_CHUNK", "0"))
+        self.cudnn_benchmark = bool(int(_os.environ.get("PFB_CUDNN_BENCHMARK", "1")))
         self._engine: Optional[RaftEngine] = None
         self._build_networks()
 
@@ -107,11 +108,10 @@ class RAFT(BaseModel):
                 return net.forward_pm(x)
             return torch.cat([net.forward_pm(x[i : i + n]) for i in range(0, x.shape[0], n)], dim=0)
 
-        if frames.dtype == torch.float32 and self.strict_fp32:
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                fmaps = run(self.fnet, frames)
-                cnet = run(self.cnet, frames[:B])
-        else:
+        # cuDNN autotuning: its heuristics pick an fp32 SIMT kernel for the strided 96->128 convolutions of layer3
+        # (ncu launch list r01_launches_v7); benchmark mode selects per shape once.
+        strict = frames.dtype == torch.float32 and self.strict_fp32
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.cudnn_benchmark, allow_tf32=not strict):
             fmaps = run(self.fnet, frames)
             cnet = run(self.cnet, frames[:B])
         return fmaps[:B], fmaps[B:], cnet
