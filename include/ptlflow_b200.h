@@ -120,8 +120,10 @@ typedef enum {
                           out(fp32) = coords1 - grid               raft.py:174-178          */
   PFB_EPI_RELU_APPEND_FLOW = 5, /* relu into cols [0,Cout) and copy flow(fp32 [.,2]) into the
                           next two columns                          update.py:111-112      */
-  PFB_EPI_AXPY = 6     /* out = residual + scale * (acc + bias); residual = aux_h[p * hidden + n]
+  PFB_EPI_AXPY = 6,    /* out = residual + scale * (acc + bias); residual = aux_h[p * hidden + n]
                           (GMA Aggregate: fmap + gamma * attn@v)    gma_utils.py:101-113   */
+  PFB_EPI_LINEAR_F32 = 7 /* out(fp32) = scale * (acc + bias): per-tap partial products of the flow head's
+                          last convolution, summed over the 3x3 neighbourhood by pfb_flow_tap_gather */
 } pfb_epilogue;
 
 typedef struct {
@@ -195,6 +197,12 @@ PFB_API int pfb_softmax_rows(void* x, size_t rows, int cols, pfb_dtype dtype, pf
 /* [B, HW, C] pixel-major -> [B, C, HW_pad] (zero padded): K-major operand for the attn @ v GEMM */
 PFB_API int pfb_transpose_pm(const void* in, void* out, int B, int HW, int C, int HW_pad, pfb_dtype dtype, pfb_stream stream);
 
+/* Flow head conv2 (3x3, C -> 2) as "1x1 GEMM to 18 tap-products, then gather": taps [B,H,W,tstride] fp32 holds
+ * T[p][tap*2+o] = <W2[o,:,tap], x(p)>; delta(p)[o] = bias[o] + sum_tap T[p + tap][tap*2+o] (zero outside the image);
+ * coords += delta, flow = coords - grid.        update.py:9,14 ; raft.py:174-178 */
+PFB_API int pfb_flow_tap_gather(const float* taps, int tstride, const float* bias, float* coords, float* flow, int B, int H, int W,
+                                pfb_stream stream);
+
 /* cnet output [B,H,W,hd+cd] -> net = tanh(first hd), inp = relu(rest)     raft.py:155-158 */
 PFB_API int pfb_context_split(const void* cnet, void* net, void* inp, int B, int H, int W, int hidden, int context,
                       pfb_dtype dtype, pfb_stream stream);
@@ -210,6 +218,7 @@ typedef enum {
   PFB_L_GRU_ZR1, PFB_L_GRU_Q1, PFB_L_GRU_ZR2, PFB_L_GRU_Q2,
   PFB_L_FLOW1, PFB_L_FLOW2, PFB_L_MASK1, PFB_L_MASK2,
   PFB_L_AGG_V, /* GMA Aggregate.to_v (1x1, no bias) */
+  PFB_L_FLOW2T, /* flow_head.conv2 re-expressed as a 1x1 layer with 18 = 9 taps x 2 outputs (row = tap*2+o) */
   PFB_L_COUNT
 } pfb_layer_id;
 

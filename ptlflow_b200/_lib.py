@@ -21,10 +21,10 @@ PFB_MAX_SRC = 4
 F32, F16, BF16 = 0, 1, 2
 _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
-EPI_LINEAR, EPI_RELU, EPI_GRU_ZR, EPI_GRU_Q, EPI_FLOW, EPI_RELU_APPEND_FLOW, EPI_AXPY = range(7)
+EPI_LINEAR, EPI_RELU, EPI_GRU_ZR, EPI_GRU_Q, EPI_FLOW, EPI_RELU_APPEND_FLOW, EPI_AXPY, EPI_LINEAR_F32 = range(8)
 
 (L_CONVC1, L_CONVC2, L_CONVF1, L_CONVF2, L_CONV, L_GRU_ZR1, L_GRU_Q1, L_GRU_ZR2, L_GRU_Q2,
- L_FLOW1, L_FLOW2, L_MASK1, L_MASK2, L_AGG_V, L_COUNT) = range(15)
+ L_FLOW1, L_FLOW2, L_MASK1, L_MASK2, L_AGG_V, L_FLOW2T, L_COUNT) = range(16)
 
 
 class ConvSrc(C.Structure):
@@ -97,6 +97,7 @@ SIGNATURES = {
     "pfb_upflow8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_softmax_rows": (_I, [_P, C.c_size_t, _I, _I, _S]),
     "pfb_transpose_pm": (_I, [_P, _P, _I, _I, _I, _I, _I, _S]),
+    "pfb_flow_tap_gather": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _S]),
     "pfb_context_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_init_coords": (_I, [_P, _P, _I, _I, _I, _S]),
     "pfb_raft_workspace_bytes": (C.c_size_t, [C.POINTER(RaftCfg)]),

@@ -141,6 +141,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvDev a) {
           reinterpret_cast<T*>(a.out)[(size_t)p * a.out_stride + a.out_offset + n] = from_f32<T>((1.f - z) * h + z * q);
           break;
         }
+        case PFB_EPI_LINEAR_F32:
+          reinterpret_cast<float*>(a.out)[(size_t)p * a.out_stride + a.out_offset + n] = v * a.scale;
+          break;
         case PFB_EPI_AXPY: {
           float res = to_f32(reinterpret_cast<const T*>(a.aux_h)[(size_t)p * hd + n]);
           reinterpret_cast<T*>(a.out)[(size_t)p * a.out_stride + a.out_offset + n] = from_f32<T>(res + a.scale * v);
@@ -210,7 +213,7 @@ extern "C" PFB_API int pfb_conv2d(const pfb_conv_params* p, pfb_stream stream) {
                   "conv2d: bad source %d", i);
   }
   switch (p->epilogue) {
-    case PFB_EPI_LINEAR: case PFB_EPI_RELU: break;
+    case PFB_EPI_LINEAR: case PFB_EPI_RELU: case PFB_EPI_LINEAR_F32: break;
     case PFB_EPI_AXPY:
       PFB_CHECK_ARG(p->aux_h && p->hidden >= p->Cout, "conv2d: AXPY needs aux_h (residual) with stride hidden >= Cout");
       break;

@@ -140,6 +140,31 @@ __global__ void __launch_bounds__(128, 3) conv_flow7x7_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// delta(p)[o] = bias[o] + sum over the 3x3 neighbourhood of the per-tap products T[p + tap][tap*2 + o]
+__global__ void flow_tap_gather_kernel(const float* __restrict__ taps, int tstride, const float* __restrict__ bias,
+                                       float* __restrict__ coords, float* __restrict__ flow, int B, int H, int W) {
+  const int P = B * H * W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int x = p % W, y = (p / W) % H, b = p / (W * H);
+  float d0 = bias ? bias[0] : 0.f, d1 = bias ? bias[1] : 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float2 t = *reinterpret_cast<const float2*>(taps + ((size_t)(b * H + iy) * W + ix) * tstride + 2 * tap);
+      d0 += t.x;
+      d1 += t.y;
+    }
+  }
+  const float c0 = coords[2 * (size_t)p] + d0, c1 = coords[2 * (size_t)p + 1] + d1;
+  coords[2 * (size_t)p] = c0;
+  coords[2 * (size_t)p + 1] = c1;
+  flow[2 * (size_t)p] = c0 - (float)x;
+  flow[2 * (size_t)p + 1] = c1 - (float)y;
+}
+
+// ---------------------------------------------------------------------------------------------
 struct SrcSplit {
   int n;
   int ch[PFB_MAX_SRC];
@@ -246,6 +271,16 @@ extern "C" PFB_API int pfb_pack_conv_weight_kmajor(const void* src, void* dst, i
   ProfScope prof(KC_MISC, as_stream(stream));
   pack_kmajor_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, dst, Cout, Cin, KH, KW, Cout_pad_k, row_offset, sp, Cin_pad,
                                                             (int)src_dtype, (int)dst_dtype);
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}
+
+extern "C" PFB_API int pfb_flow_tap_gather(const float* taps, int tstride, const float* bias, float* coords, float* flow, int B, int H,
+                                           int W, pfb_stream stream) {
+  PFB_CHECK_ARG(taps && coords && flow && B > 0 && H > 0 && W > 0 && tstride >= 18 && tstride % 2 == 0, "flow_tap_gather: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  ProfScope prof(KC_CONV, s);
+  flow_tap_gather_kernel<<<ceil_div(B * H * W, 256), 256, 0, s>>>(taps, tstride, bias, coords, flow, B, H, W);
   PFB_LAUNCH_CHECK();
   return PFB_OK;
 }

@@ -351,6 +351,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
+          case PFB_EPI_LINEAR_F32: {  // fp32 output (16-byte aligned rows: out_stride % 4 == 0)
+            float* o32 = reinterpret_cast<float*>(a.out) + p * a.out_stride + a.out_offset + n;
+            const int valid = a.Cout - n;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (4 * q + 4 <= valid)
+                reinterpret_cast<float4*>(o32)[q] = make_float4(v[4 * q] * a.scale, v[4 * q + 1] * a.scale, v[4 * q + 2] * a.scale, v[4 * q + 3] * a.scale);
+              else
+                for (int e = 4 * q; e < 4 * q + 4; ++e)
+                  if (e < valid) o32[e] = v[e] * a.scale;
+            break;
+          }
           case PFB_EPI_AXPY: {  // residual + scale * acc   (residual = aux_h[p * hidden + n])
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -450,6 +462,9 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
   if (cin_pad != p->Cin_pad) return false;
   switch (p->epilogue) {
     case PFB_EPI_LINEAR: case PFB_EPI_RELU: case PFB_EPI_RELU_APPEND_FLOW: break;
+    case PFB_EPI_LINEAR_F32:
+      if (p->out_stride % 4 || p->out_offset % 4) return false;
+      break;
     case PFB_EPI_AXPY:
       if (!p->aux_h || p->hidden % 8 || p->Cout % 32) return false;
       break;

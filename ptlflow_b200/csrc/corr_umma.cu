@@ -11,6 +11,8 @@
 // CTA = 6 warps: 0-3 epilogue (TMEM lane quarter = warp id), 4 = TMA producer, 5 = MMA issuer / TMEM owner.
 // A (this CTA's 128 queries) is loaded once; B patches stream through a 2-deep ring; two 128-column TMEM
 // accumulators let the epilogue of patch i overlap the MMAs of patch i+1.
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace pfb {
@@ -74,14 +76,18 @@ __device__ __forceinline__ void store_row(T* dst, const float (&v)[N], int valid
 
 template <typename T>
 __global__ void __launch_bounds__(192, 1)
-corr_volume_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, PyrOut out,
-                        int H, int W, int N, int kchunks, int levels, float scale, int n_groups, int ab_fmt) {
+corr_volume_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmO, PyrOut out, int H, int W, int N, int kchunks, int levels,
+                        float scale, int n_groups, int ab_fmt, int tma_store) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                     // kchunks tiles
   uint8_t* sB = smem + kchunks * kTileBytes;              // 2 stages x kchunks tiles
-  CorrBars* bars = reinterpret_cast<CorrBars*>(sB + 2 * kchunks * kTileBytes);
+  // level-0 staging for the TMA store: [8 patch rows][128 queries][16 cols] (32 KB); a thread writes its query's
+  // 32-byte row segments at (hh * 128 + row) * 32 -> consecutive lanes on consecutive segments, no bank conflicts
+  uint8_t* sC = sB + 2 * kchunks * kTileBytes;
+  CorrBars* bars = reinterpret_cast<CorrBars*>(sC + (tma_store ? 8 * 128 * 32 : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, group = blockIdx.y, b = blockIdx.z;
@@ -164,6 +170,10 @@ corr_volume_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int ph = tile / PW, pw = tile - ph * PW;
       mbar_wait(&bars->acc_full[s], use & 1);
       tc_fence_after();
+      if (tma_store && i > 0) {  // the previous tile's bulk store must have drained the staging buffer
+        if (threadIdx.x == 0) tma_store_wait_read();
+        named_barrier_sync(1, 128);
+      }
       const uint32_t taddr = tmem_base + s * 128 + ((uint32_t)(warp * 32) << 16);
       float l1prev[8], l2prev[4];
 #pragma unroll
@@ -174,7 +184,10 @@ corr_volume_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         float v[2][16];
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e >> 4][e & 15] = rt<T>(__uint_as_float(r[e]) * scale);
-        if (row_ok) {
+        if (tma_store) {
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) store_row<T, 16>(reinterpret_cast<T*>(sC + ((2 * c + rr) * 128 + row) * 32), v[rr], 16, true);
+        } else if (row_ok) {
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
             const int h2 = ph * 8 + 2 * c + rr, w2 = pw * 16;
@@ -216,7 +229,16 @@ corr_volume_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty[s]);
+      if (tma_store) {
+        fence_proxy_async();         // generic-proxy writes -> visible to the async (TMA) proxy
+        named_barrier_sync(1, 128);  // the four epilogue warps
+        if (threadIdx.x == 0) {
+          tma_store_4d(&tmO, sC, pw * 16, m_tile * 128, ph * 8, b);  // clipped at W / N / H by the TMA unit
+          tma_store_commit();
+        }
+      }
     }
+    if (tma_store && threadIdx.x == 0) tma_store_wait_read();
   }
   tc_fence_before();
   __syncthreads();
@@ -252,22 +274,35 @@ int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, in
   }
   PyrOut out{};
   for (int l = 0; l < L; ++l) out.ptr[l] = pyr[l];
+  // level 0 leaves through TMA bulk stores (full-sector writes issued by the copy engine instead of 16-byte
+  // per-thread stores to 128 different query maps); needs 16-byte aligned target rows
+  static const int env_tma = getenv("PFB_VOLUME_TMA_STORE") ? atoi(getenv("PFB_VOLUME_TMA_STORE")) : 1;
+  const int tma_store = (env_tma && (W % 8) == 0) ? 1 : 0;
+  CUtensorMap tmO = tmA;
+  if (tma_store) {
+    // dims ordered (w, query, h, b) so that the shared-memory box is [h][query][w]
+    uint64_t dims[4] = {(uint64_t)W, (uint64_t)N, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)H * W * 2, (uint64_t)W * 2, (uint64_t)N * H * W * 2};
+    uint32_t box[4] = {16, 128, 8, 1};
+    int rc = make_tensor_map_linear(&tmO, pyr[0], dt, 4, dims, str, box);
+    if (rc) return rc;
+  }
   const int m_tiles = ceil_div(N, 128);
   const int n_tiles = ceil_div(W, 16) * ceil_div(H, 8);
   // enough CTAs for ~2 waves of the machine; each CTA keeps its A tile and walks its share of patches
   int groups = ceil_div(2 * sm_count(), m_tiles * B);
   if (groups < 1) groups = 1;
   if (groups > n_tiles) groups = n_tiles;
-  const size_t smem = (size_t)3 * kchunks * kTileBytes + sizeof(CorrBars) + 1024;
+  const size_t smem = (size_t)3 * kchunks * kTileBytes + (tma_store ? 8 * 128 * 32 : 0) + sizeof(CorrBars) + 1024;
   const float scale = 1.0f / sqrtf((float)C);
   dim3 grid(m_tiles, groups, B);
   ProfScope prof(KC_VOLUME, s);
   if (dt == PFB_F16) {
     PFB_CUDA(cudaFuncSetAttribute(corr_volume_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_volume_umma_kernel<__half><<<grid, 192, smem, s>>>(tmA, tmB, out, H, W, N, kchunks, L, scale, groups, 0);
+    corr_volume_umma_kernel<__half><<<grid, 192, smem, s>>>(tmA, tmB, tmO, out, H, W, N, kchunks, L, scale, groups, 0, tma_store);
   } else {
     PFB_CUDA(cudaFuncSetAttribute(corr_volume_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    corr_volume_umma_kernel<__nv_bfloat16><<<grid, 192, smem, s>>>(tmA, tmB, out, H, W, N, kchunks, L, scale, groups, 1);
+    corr_volume_umma_kernel<__nv_bfloat16><<<grid, 192, smem, s>>>(tmA, tmB, tmO, out, H, W, N, kchunks, L, scale, groups, 1, tma_store);
   }
   PFB_LAUNCH_CHECK();
   return PFB_OK;

@@ -16,6 +16,7 @@ struct Workspace {
   // element strides (channels per pixel) and byte offsets inside the caller's workspace
   int planes, corr_stride;
   size_t off_corr, off_cor1, off_corflo, off_flo1, off_motion, off_z, off_rh, off_fh, off_mh, off_mask, off_flow;
+  size_t off_taps;          // flow head conv2 per-tap products [P][32] fp32 (tensor-core path)
   size_t off_vbuf, off_vT;  // gma: to_v(motion) [P][128] and its per-sample transpose [B][128][n_pad]
   int n_pad;
   size_t total;
@@ -51,6 +52,7 @@ static Workspace plan(const pfb_raft_cfg* c) {
   w.off_mh = take(c->variant != 1 ? P * 256 * es : 0);
   w.off_mask = take(c->variant != 1 ? P * 576 * es : 0);
   w.off_flow = take(P * 2 * sizeof(float));
+  w.off_taps = take(c->variant != 1 ? P * 32 * sizeof(float) : 0);
   w.n_pad = (int)align_up((size_t)c->H * c->W, 64);
   w.off_vbuf = take(c->variant == 2 ? P * 128 * es : 0);
   w.off_vT = take(c->variant == 2 ? (size_t)c->B * 128 * w.n_pad * es : 0);
@@ -195,7 +197,15 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
 
   // ---- heads (update.py:6-14, :138-152) ----
   PFB_TRY(run_conv(x, PFB_L_FLOW1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, fh, ws.c_fh, 0));
-  PFB_TRY(run_conv(x, PFB_L_FLOW2, {src_of(fh, ws.c_fh, ws.c_fh)}, PFB_EPI_FLOW, flow, 2, 0));
+  const pfb_layer& LT = x.w->layers[PFB_L_FLOW2T];
+  if (c->variant != 1 && c->dtype != PFB_F32 && c->impl != 1 && LT.weight_k) {
+    // tensor-core form of the 3x3 -> 2 convolution: one 1x1 GEMM to the 18 (tap, output) products, then a 9-tap gather
+    float* taps = reinterpret_cast<float*>(x.at(ws.off_taps));
+    PFB_TRY(run_conv(x, PFB_L_FLOW2T, {src_of(fh, ws.c_fh, ws.c_fh)}, PFB_EPI_LINEAR_F32, taps, 32, 0));
+    PFB_TRY(pfb_flow_tap_gather(taps, 32, x.w->layers[PFB_L_FLOW2].bias, x.b->coords, flow, c->B, c->H, c->W, (pfb_stream)x.s));
+  } else {
+    PFB_TRY(run_conv(x, PFB_L_FLOW2, {src_of(fh, ws.c_fh, ws.c_fh)}, PFB_EPI_FLOW, flow, 2, 0));
+  }
   if (mask_out && c->variant != 1) {
     void* mh = x.at(ws.off_mh);
     PFB_TRY(run_conv(x, PFB_L_MASK1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, mh, 256, 0));

@@ -20,8 +20,20 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static int make_map_impl(CUtensorMap* out, const void* base, pfb_dtype dt, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
 int make_tensor_map(CUtensorMap* out, const void* base, pfb_dtype dt, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_map_impl(out, base, dt, rank, dims, strides_bytes, box, true);
+}
+int make_tensor_map_linear(CUtensorMap* out, const void* base, pfb_dtype dt, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_map_impl(out, base, dt, rank, dims, strides_bytes, box, false);
+}
+
+static int make_map_impl(CUtensorMap* out, const void* base, pfb_dtype dt, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -42,9 +54,11 @@ int make_tensor_map(CUtensorMap* out, const void* base, pfb_dtype dt, int rank, 
       gstr[i - 1] = strides_bytes[i - 1];
     }
   }
-  PFB_CHECK_ARG(box[0] * 2 == 128, "tensor map: inner box must span 128 bytes for SWIZZLE_128B");
+  if (swizzle128) PFB_CHECK_ARG(box[0] * 2 == 128, "tensor map: inner box must span 128 bytes for SWIZZLE_128B");
+  else PFB_CHECK_ARG((box[0] * 2) % 16 == 0, "tensor map: inner box must be a multiple of 16 bytes");
   CUresult r = enc(out, dt == PFB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
-                   const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu ...)", (int)r, rank,

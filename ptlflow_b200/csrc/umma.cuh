@@ -77,6 +77,19 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// ---------------------------------------------------------------- TMA stores (shared -> global, bulk async group)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores issued so far have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // In a 2-CTA cluster the even CTA is the MMA leader.  Shared-window addresses of the two CTAs differ in bit 24
 // ("peer bit"), so clearing it turns any local barrier address into the leader's copy of the same barrier.
@@ -255,5 +268,8 @@ __device__ __forceinline__ bool elect_one() {
 // swizzle, zero fill for out-of-bounds elements (this is what gives "same" conv padding for free).
 int make_tensor_map(CUtensorMap* out, const void* base, pfb_dtype dt, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
+// same without swizzle (dense box in shared memory; inner box extent any multiple of 16 bytes) -- TMA stores
+int make_tensor_map_linear(CUtensorMap* out, const void* base, pfb_dtype dt, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box);
 
 }  // namespace pfb

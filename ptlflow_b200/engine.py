@@ -50,6 +50,13 @@ class RaftEngine:
             layers[_lib.L_GRU_Q2] = P(gsrc, gru.convq2)
             layers[_lib.L_FLOW1] = P([hd], fh.conv1)
             layers[_lib.L_FLOW2] = P([256], fh.conv2)
+            if dtype != torch.float32:
+                # conv2 as a 1x1 layer producing the 9 x 2 per-tap products (row = tap*2 + o); bias is added by the gather
+                class _Taps:
+                    def __init__(self, w):
+                        self.weight, self.bias = w.detach().permute(2, 3, 0, 1).reshape(18, w.shape[1], 1, 1).contiguous(), None
+
+                layers[_lib.L_FLOW2T] = P([256], _Taps(fh.conv2.weight))
             layers[_lib.L_MASK1] = P([hd], ub.mask[0])
             layers[_lib.L_MASK2] = P([256], ub.mask[2])
         else:  # raft_small: odd channel counts (96 / 82 / 146) -> SIMT kernels only

@@ -135,7 +135,7 @@ class PackedConv:
         if src_channels is not None and dtype != torch.float32:
             assert sum(src_channels) == self.Cin
             self.Cin_pad = sum((c + 63) // 64 * 64 for c in src_channels)
-            self.Cout_pad_k = (self.Cout + 31) // 32 * 32 if self.Cout >= 32 else 16
+            self.Cout_pad_k = (self.Cout + 31) // 32 * 32 if self.Cout > 16 else 16
             self.weight_k = torch.zeros((self.KH * self.KW, self.Cout_pad_k, self.Cin_pad), dtype=dtype, device=device)
         self.bias = torch.zeros((max(self.Cout_pad, self.Cout_pad_k, 32),), dtype=torch.float32, device=device)
         lib = load()
