@@ -488,11 +488,8 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
 template <typename T, int CG>
 static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const ConvUmmaArgs& a, int grid, size_t smem,
                             cudaStream_t s) {
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  // per launch (cheap, and correct when one process drives several devices)
+  PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(320);
