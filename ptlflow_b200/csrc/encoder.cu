@@ -80,6 +80,20 @@ __global__ void __launch_bounds__(256) inorm_stats_kernel(const T* __restrict__ 
         q[k] = fmaf(v[k], v[k], q[k]);
       }
     }
+  }
+  // lanes of a warp that own the same channel octet are c8n apart: fold them with shuffles first (when c8n divides
+  // 32), so the shared-memory atomics see 32 / c8n times fewer, far less contended, updates
+  const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32 && (blockDim.x % c8n) == 0;
+  if (pow2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      for (int o = c8n; o < 32; o <<= 1) {
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+        q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+      }
+    }
+  }
+  if (pl < lanes && (!pow2 || (threadIdx.x & 31) < c8n)) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       atomicAdd(&acc[8 * co + k], s[k]);
