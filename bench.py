@@ -316,9 +316,15 @@ def run_ours(args):
     roofline = None
     if dominant == "conv":
         e = kernels["conv"]
-        roofline = {"kernel": "update-block conv (implicit GEMM)", "bound": "tensor", "achieved": e["tflops"],
+        traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of the same command
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_umma_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = round(json.load(f)["dram_bytes_per_launch"])
+        roofline = {"kernel": "update-block conv (implicit GEMM, tcgen05)", "bound": "tensor", "achieved": e["tflops"],
                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": e["frac_of_bf16_sustained_peak"],
-                    "traffic": None, "peak_source": peaks["_source"] + ", sustained bf16 GEMM"}
+                    "traffic": traffic, "peak_source": peaks["_source"] + ", sustained bf16 GEMM",
+                    "algorithmic_flops_per_launch": round(work["conv"]["flops"] / max(1, e["launches_per_step"]))}
     elif dominant is not None and "algorithmic_gbs" in kernels[dominant]:
         e = kernels[dominant]
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": e["algorithmic_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
