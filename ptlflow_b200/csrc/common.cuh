@@ -79,6 +79,30 @@ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 int sm_count();
 
 // kernel classes for launch accounting / live per-class timing (prof.cu)
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// The refinement loop is ~25 short dependent launches per iteration; the kernel-to-kernel hand-over (grid drain,
+// launch latency, prologue of the next kernel) is ~2 us each.  Kernels on that path are launched with
+// programmaticStreamSerialization: they may be scheduled while the previous grid drains, do their data-independent
+// prologue, and block in pdl_wait() until the previous grid has completed and flushed.  pdl_trigger() lets the
+// NEXT kernel in the stream do the same relative to this one.  PFB_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 enum KernelClass { KC_VOLUME = 0, KC_POOL, KC_LOOKUP, KC_ONTHEFLY, KC_CONV, KC_UPSAMPLE, KC_MISC, KC_COUNT };
 class ProfScope {
  public:

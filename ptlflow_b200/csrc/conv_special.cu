@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(128, 3) conv_flow7x7_kernel(const float* __res
                                                            const T* __restrict__ w /*[49][2][Cout_pad]*/, int Cout,
                                                            int Cout_pad, const float* __restrict__ bias,
                                                            T* __restrict__ out, int out_stride, int out_offset) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float2 patch[FTH + 6][FTW + 6];
   const int PW = (W + FTW - 1) / FTW, PH = (H + FTH - 1) / FTH;
   int t = blockIdx.x;
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(128, 3) conv_flow7x7_kernel(const float* __res
 // delta(p)[o] = bias[o] + sum over the 3x3 neighbourhood of the per-tap products T[p + tap][tap*2 + o]
 __global__ void flow_tap_gather_kernel(const float* __restrict__ taps, int tstride, const float* __restrict__ bias,
                                        float* __restrict__ coords, float* __restrict__ flow, int B, int H, int W) {
+  pdl_wait();
+  pdl_trigger();
   const int P = B * H * W;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -227,7 +231,7 @@ bool conv_flow7x7_supported(const pfb_conv_params* p) {
 template <typename T, int FTH, int FTW>
 static void launch_flow7x7(const pfb_conv_params* p, cudaStream_t s) {
   dim3 grid(ceil_div(p->W, FTW) * ceil_div(p->H, FTH) * p->B, ceil_div(p->Cout, 128));
-  conv_flow7x7_kernel<T, FTH, FTW><<<grid, 128, 0, s>>>((const float*)p->src[0].ptr, p->B, p->H, p->W, (const T*)p->weight, p->Cout,
+  launch_pdl(conv_flow7x7_kernel<T, FTH, FTW>, dim3(grid), dim3(128), 0, s, (const float*)p->src[0].ptr, p->B, p->H, p->W, (const T*)p->weight, p->Cout,
                                                         p->Cout_pad, p->bias, (T*)p->out, p->out_stride, p->out_offset);
 }
 
@@ -280,7 +284,7 @@ extern "C" PFB_API int pfb_flow_tap_gather(const float* taps, int tstride, const
   PFB_CHECK_ARG(taps && coords && flow && B > 0 && H > 0 && W > 0 && tstride >= 18 && tstride % 2 == 0, "flow_tap_gather: bad arguments");
   cudaStream_t s = as_stream(stream);
   ProfScope prof(KC_CONV, s);
-  flow_tap_gather_kernel<<<ceil_div(B * H * W, 256), 256, 0, s>>>(taps, tstride, bias, coords, flow, B, H, W);
+  launch_pdl(flow_tap_gather_kernel, dim3(ceil_div(B * H * W, 256)), dim3(256), 0, s, taps, tstride, bias, coords, flow, B, H, W);
   PFB_LAUNCH_CHECK();
   return PFB_OK;
 }

@@ -17,6 +17,7 @@
 // chosen per shape to minimise padding (128x1 rows for W = 128: 440 tiles = 2.97 waves of 148 SMs).
 // The epilogue fuses bias + ReLU / sigmoid / tanh + the GRU gate arithmetic of
 // ptlflow/models/raft/update.py:58-73 and writes pixel-major f16/bf16 with 16-byte stores.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "umma.cuh"
@@ -25,7 +26,7 @@ namespace pfb {
 using namespace sm100;
 
 constexpr int kATileBytes = 128 * 128;
-constexpr int kMaxAStages = 6, kMaxBStages = 8;
+constexpr int kMaxAStages = 8, kMaxBStages = 32;
 
 struct __align__(8) ConvBars {
   uint64_t a_full[kMaxAStages];
@@ -54,6 +55,7 @@ struct ConvUmmaArgs {
   // address, so TMA writes and UMMA reads stay consistent.  Otherwise every tap loads its own patch.
   int halo;
   int a_stages, a_slot_bytes, a_tx_bytes, b_stages, b_slot_bytes;
+  int b_group, b_tap_bytes;      // weight stage = b_group consecutive taps of one activation patch (1, or all of them)
   int desc_base_offset_mode;     // experiment knob: 1 = put (addr >> 7) & 7 into the descriptor base_offset field
   const float* bias;
   int epilogue;
@@ -65,7 +67,10 @@ struct ConvUmmaArgs {
   int hidden;
   const float* flow;
   int ab_fmt;
+  unsigned long long* trace;     // debug timeline (PFB_CONV_TRACE): 32 clock64 slots per CTA, null in production
 };
+
+#define PFB_TR(slot) do { if (a.trace && lane == 0) a.trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
 
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -110,6 +115,21 @@ __device__ __forceinline__ void load32(const T* src, float (&v)[32]) {
   }
 }
 
+// G taps x 4 K-steps of one pipeline step, straight-line (descriptor words advance by constants)
+template <int CG, int G>
+__device__ __forceinline__ void issue_taps(uint32_t d, uint32_t a_lo, uint32_t a_tap16, uint32_t b_lo, uint32_t b_tap16, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t acc) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t en = (g == 0 && kk == 0) ? acc : 1u;
+      if (CG == 2) umma_f16_lohi_2cta(d, a_lo + g * a_tap16 + 2 * kk, b_lo + g * b_tap16 + 2 * kk, desc_hi, idesc, en);
+      else umma_f16_lohi(d, a_lo + g * a_tap16 + 2 * kk, b_lo + g * b_tap16 + 2 * kk, desc_hi, idesc, en);
+    }
+  }
+}
+
 // CG = 1: one CTA per MMA (M = 128).  CG = 2: CTA pairs (cta_group::2, M = 256): the pair shares every weight
 // tile -- each CTA stages only half of its rows and the tensor cores of both SMs read both halves -- which
 // halves the shared-memory traffic per MMA, the limiter of the single-CTA version.
@@ -124,6 +144,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   ConvBars* bars = reinterpret_cast<ConvBars*>(smemB + a.b_stages * a.b_slot_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a.trace && threadIdx.x == 0) {
+    a.trace[blockIdx.x * 32 + 0] = global_timer_ns();
+    a.trace[blockIdx.x * 32 + 1] = clock64();
+  }
   int chunks = 0;
   for (int s = 0; s < a.nsrc; ++s) chunks += a.src_chunks[s];
   const int tiles_m = a.tiles_x * a.tiles_y * a.B;
@@ -159,6 +183,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // PDL: everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's drain
+  pdl_wait();
+  pdl_trigger();
+  if (warp == 0) PFB_TR(2);
 
   // work item j -> (n tile, image, tile row, tile col) of THIS CTA; n-tile major so concurrent CTAs share the weight
   // tile in L2.  In pair mode the two CTAs take adjacent M tiles; a missing partner tile decodes to b == B
@@ -183,8 +211,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       const uint32_t btx = a.NT * 128;  // bytes of the whole weight tile (both halves in pair mode)
       const int brow = rank * (a.NT / CG);  // this CTA stages rows [brow, brow + NT / CG) of the weight tile
       // ring positions advance incrementally (stage index + phase bit): no integer division on the issue path
-      int sta = 0, stb = 0;
+      int sta = 0, stb = 0, bg = 0;
       uint32_t pha = 0, phb = 0;
+      PFB_TR(3);
       for (int w = group0; w < a.n_work; w += group_stride) {
         int n0, b, y0, x0;
         decode(w, n0, b, y0, x0);
@@ -195,7 +224,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             int wrow = 0;  // (ky * KW + kx) * Cout_pad_k
             for (int ky = 0; ky < a.KH; ++ky) {
               for (int kx = 0; kx < a.KW; ++kx) {
-                if (kx == 0 || !a.halo) {  // activation patch: once per (chunk, ky) in halo mode, else once per tap
+                // activation patch: once per (chunk, ky) with the x halo, once per chunk with the y halo, else per tap
+                if (a.halo == 0 || (a.halo == 1 && kx == 0) || (a.halo == 2 && ky == 0)) {
                   mbar_wait(&bars->a_empty[sta], pha ^ 1);
                   if (elect_one()) {
                     // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
@@ -210,20 +240,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                   __syncwarp();
                   if (++sta == a.a_stages) { sta = 0; pha ^= 1; }
                 }
-                mbar_wait(&bars->b_empty[stb], phb ^ 1);
+                // weight stage: b_group consecutive taps of this patch share one barrier (fewer, larger pipeline steps)
+                if (bg == 0) mbar_wait(&bars->b_empty[stb], phb ^ 1);
                 if (elect_one()) {
-                  if (rank == 0) mbar_arrive_expect_tx(&bars->b_full[stb], btx);
-                  if (CG == 2) tma_load_2d_2cta(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0 + brow);
-                  else tma_load_2d(smemB + stb * a.b_slot_bytes, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0);
+                  if (rank == 0 && bg == 0) mbar_arrive_expect_tx(&bars->b_full[stb], btx * a.b_group);
+                  uint8_t* dstB = smemB + stb * a.b_slot_bytes + bg * a.b_tap_bytes;
+                  if (CG == 2) tma_load_2d_2cta(dstB, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0 + brow);
+                  else tma_load_2d(dstB, &tmW, &bars->b_full[stb], kidx * 64, wrow + n0);
                 }
                 __syncwarp();
                 wrow += a.Cout_pad_k;
-                if (++stb == a.b_stages) { stb = 0; phb ^= 1; }
+                if (++bg == a.b_group) {
+                  bg = 0;
+                  if (++stb == a.b_stages) { stb = 0; phb ^= 1; }
+                }
               }
             }
           }
         }
       }
+      PFB_TR(4);
     }
   } else if (warp == 5) {
     // ================= MMA issuer =================
@@ -242,8 +278,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       const uint32_t b_lo0 = ((smem_u32(smemB) & 0x3FFFF) >> 4) | (1u << 16);
       const uint32_t bar_a_full = smem_u32(&bars->a_full[0]), bar_a_empty = smem_u32(&bars->a_empty[0]);
       const uint32_t bar_b_full = smem_u32(&bars->b_full[0]), bar_b_empty = smem_u32(&bars->b_empty[0]);
-      const int kw_halo = a.halo ? a.KW : 1;             // taps served by one activation patch
-      const int groups = chunks * a.KH * (a.halo ? 1 : a.KW);  // activation patches per tile
+      const int kw_halo = a.halo == 1 ? a.KW : (a.halo == 2 ? a.KH : 1);  // taps served by one activation patch
+      const int groups = chunks * (a.halo == 1 ? a.KH : (a.halo == 2 ? 1 : a.KH * a.KW));  // patches per tile
+      const uint32_t tap_step16 = a.halo == 2 ? (uint32_t)a.TW * 8u : 8u;  // descriptor advance per tap (16-B units)
+      const uint32_t b_tap16 = (uint32_t)a.b_tap_bytes >> 4;
       int sa = 0, sb = 0, i = 0;
       uint32_t pha = 0, phb = 0;
       uint32_t a_lo = a_lo0, b_lo = b_lo0;
@@ -251,23 +289,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         const int t = i & 1;
         mbar_wait(&bars->acc_empty[t], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (i < 3) PFB_TR(9 + i);
         const uint32_t d = tmem_base + t * a.acc_stride;
         uint32_t acc = 0;  // first MMA of the tile overwrites the accumulator
         for (int g = 0; g < groups; ++g) {
-          mbar_wait_addr(bar_a_full + 8 * sa, pha);
-          for (int kx = 0; kx < kw_halo; ++kx) {
-            mbar_wait_addr(bar_b_full + 8 * sb, phb);
+          mbar_wait_uniform(bar_a_full + 8 * sa, pha);
+          if (i == 0 && g == 0) PFB_TR(5);
+          for (int kx = 0; kx < kw_halo; kx += a.b_group) {
+            mbar_wait_uniform(bar_b_full + 8 * sb, phb);
             tc_fence_after();
-            const uint32_t al = a_lo + 8 * kx;  // halo: tap kx starts kx pixel rows (128 B) into the patch
+            const uint32_t al = a_lo + tap_step16 * kx;  // x halo: +1 pixel row (128 B) per tap; y halo: +TW rows
             if (elect_one()) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if (CG == 2) umma_f16_lohi_2cta(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, kk == 0 ? acc : 1u);
-                else umma_f16_lohi(d, al + 2 * kk, b_lo + 2 * kk, desc_hi, idesc, kk == 0 ? acc : 1u);
+              // straight-line issue of the whole group: the per-step overhead of this single thread (barrier poll,
+              // election, R->UR moves, ring bookkeeping: ~65 SASS instructions, ~500 clk) is what paced the N <= 192
+              // layers at 4 MMAs per step (PFB_CONV_TRACE timelines); 12-20 MMAs per step amortise it.
+              switch (a.b_group) {
+                case 5: issue_taps<CG, 5>(d, al, tap_step16, b_lo, b_tap16, desc_hi, idesc, acc); break;
+                case 3: issue_taps<CG, 3>(d, al, tap_step16, b_lo, b_tap16, desc_hi, idesc, acc); break;
+                default: issue_taps<CG, 1>(d, al, tap_step16, b_lo, b_tap16, desc_hi, idesc, acc); break;
               }
               if (CG == 2) umma_commit_addr_2cta(bar_b_empty + 8 * sb);
               else umma_commit_addr(bar_b_empty + 8 * sb);
-              if (kx == kw_halo - 1) {
+              if (kx + a.b_group >= kw_halo) {
                 if (CG == 2) umma_commit_addr_2cta(bar_a_empty + 8 * sa);
                 else umma_commit_addr(bar_a_empty + 8 * sa);
               }
@@ -285,6 +328,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           else umma_commit(&bars->acc_full[t]);
         }
         __syncwarp();
+        if (i < 3) PFB_TR(6 + i);
       }
     }
   } else {
@@ -302,31 +346,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       const int y = y0 + (row >> a.tw_shift), x = x0 + (row & (a.TW - 1));
       const bool ok = (y < a.H) && (x < a.W) && (b < a.B);
       const size_t p = ((size_t)b * a.H + (ok ? y : 0)) * a.W + (ok ? x : 0);
-      mbar_wait(&bars->acc_full[t], tuse & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + t * a.acc_stride + ((uint32_t)(quarter * 32) << 16);
-      for (int c = group * 32; c < a.NT; c += 64) {
-        const int n = n0 + c;  // first output channel of this chunk
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        // operands that do not depend on the accumulator are requested while the TMEM load is in flight
-        float4 bb[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bb[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        uint4 hraw[4], zraw[4];
+      // Operands that do not depend on the accumulator (h, z, residual) are requested BEFORE waiting for the MMAs
+      // of this tile, and the next chunk's while the current one is processed: the ncu source view of the first
+      // version had the epilogue warps parked on these loads (exposed L2 latency, 25 % of their time), which made
+      // the GRU layers epilogue-bound (3 tiles per CTA, each epilogue ~2x the tile's MMA time).
+      const bool aux_h_any = a.epilogue == PFB_EPI_GRU_ZR || a.epilogue == PFB_EPI_GRU_Q || a.epilogue == PFB_EPI_AXPY;
+      auto issue_aux = [&](int c, uint4 (&hq)[4], uint4 (&zq)[4]) {
+        const int n = n0 + c;
         const bool need_h = ok && ((a.epilogue == PFB_EPI_GRU_ZR && n >= hd) || a.epilogue == PFB_EPI_GRU_Q ||
                                    (a.epilogue == PFB_EPI_AXPY && n + 32 <= a.Cout));
         const bool need_z = ok && a.epilogue == PFB_EPI_GRU_Q;
         if (need_h) {
           const T* hp = reinterpret_cast<const T*>(a.aux_h) + p * hd + (a.epilogue == PFB_EPI_GRU_ZR ? n - hd : n);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) hraw[q] = reinterpret_cast<const uint4*>(hp)[q];
+          for (int q = 0; q < 4; ++q) hq[q] = reinterpret_cast<const uint4*>(hp)[q];
         }
         if (need_z) {
           const T* zp = reinterpret_cast<const T*>(a.aux_z) + p * hd + n;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) zraw[q] = reinterpret_cast<const uint4*>(zp)[q];
+          for (int q = 0; q < 4; ++q) zq[q] = reinterpret_cast<const uint4*>(zp)[q];
         }
+      };
+      uint4 hnext[4], znext[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hnext[q] = znext[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (aux_h_any) issue_aux(group * 32, hnext, znext);
+      mbar_wait(&bars->acc_full[t], tuse & 1);
+      tc_fence_after();
+      if (warp == 0 && i < 3) PFB_TR(12 + i);
+      const uint32_t taddr = tmem_base + t * a.acc_stride + ((uint32_t)(quarter * 32) << 16);
+      // TMEM reads are software-pipelined too: the load of chunk c + 64 is issued as soon as chunk c has been moved
+      // to v[], and completes under the arithmetic and the stores of chunk c.
+      uint32_t r[32];
+      if (group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
+      for (int c = group * 32; c < a.NT; c += 64) {
+        const int n = n0 + c;  // first output channel of this chunk
+        float4 bb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bb[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 hraw[4], zraw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { hraw[q] = hnext[q]; zraw[q] = znext[q]; }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -335,6 +395,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb[q].y;
           v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb[q].z;
           v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb[q].w;
+        }
+        if (c + 64 < a.NT) {  // warp-uniform
+          tmem_ld_32x32(taddr + c + 64, r);
+          if (aux_h_any) issue_aux(c + 64, hnext, znext);
         }
         if (!ok) continue;
         T* out = reinterpret_cast<T*>(a.out);
@@ -429,15 +493,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == 0 && i < 3) PFB_TR(15 + i);
+      if (warp == 6 && i < 3) PFB_TR(21 + i);
       if (lane == 0) {
-        if (CG == 2) mbar_arrive_leader(&bars->acc_empty[t]);  // the leader's MMA thread owns the accumulator hand-off
+        if (CG == 2) mbar_arrive_leader_relaxed(&bars->acc_empty[t]);  // the leader's MMA thread owns the accumulator hand-off
         else mbar_arrive(&bars->acc_empty[t]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) PFB_TR(18);
   if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 0) PFB_TR(19);
+  if (a.trace && threadIdx.x == 0) a.trace[blockIdx.x * 32 + 20] = global_timer_ns();
   if (warp == 5) {
     if (CG == 2) tmem_dealloc_2cta<512>(tmem_base);
     else tmem_dealloc<512>(tmem_base);
@@ -495,13 +564,15 @@ static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, cons
   cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   PFB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, CG>, tms[0], tms[1], tms[2], tmW, a));
   return PFB_OK;
 }
@@ -523,9 +594,24 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   static const int env_halo = getenv("PFB_CONV_HALO") ? atoi(getenv("PFB_CONV_HALO")) : 1;
   static const int env_cg = getenv("PFB_CONV_CTA_PAIR") ? atoi(getenv("PFB_CONV_CTA_PAIR")) : 1;
   static const int env_desc = getenv("PFB_UMMA_DESC_MODE") ? atoi(getenv("PFB_UMMA_DESC_MODE")) : 0;
+  static const int env_vhalo = getenv("PFB_CONV_VHALO") ? atoi(getenv("PFB_CONV_VHALO")) : 1;
   a.halo = (env_halo && a.TH == 1 && p->KW > 1) ? 1 : 0;
+  if (env_vhalo && p->KW == 1 && p->KH > 1) {
+    // vertical taps: a (TH + KH - 1) x TW patch serves all KH taps of a chunk when the per-tap offset TW * 128 B keeps
+    // the 1024-byte swizzle phase (TW % 8 == 0).  Fewest tiles first, then the smallest patch.
+    long best_tiles = -1, best_patch = 0;
+    for (int tw = 64; tw >= 8; tw >>= 1) {
+      const int th = 128 / tw;
+      const long tiles = (long)ceil_div(p->W, tw) * ceil_div(p->H, th), patch = (long)(th + p->KH - 1) * tw;
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && patch < best_patch)) {
+        best_tiles = tiles; best_patch = patch; a.TW = tw; a.TH = th;
+      }
+    }
+    a.halo = 2;
+  }
   a.desc_base_offset_mode = env_desc;
-  const int patch_w = a.TW + (a.halo ? p->KW - 1 : 0);
+  const int patch_w = a.TW + (a.halo == 1 ? p->KW - 1 : 0);
+  const int patch_h = a.TH + (a.halo == 2 ? p->KH - 1 : 0);
   a.tw_shift = 0;
   while ((1 << a.tw_shift) < a.TW) ++a.tw_shift;
   a.nsrc = p->nsrc;
@@ -536,7 +622,7 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
     // dim 0 ends at the source's last real channel: a partial last 64-chunk is zero-filled by the TMA unit
     uint64_t dims[4] = {(uint64_t)(src.offset + src.channels), (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)src.stride * 2, (uint64_t)p->W * src.stride * 2, (uint64_t)p->H * p->W * src.stride * 2};
-    uint32_t box[4] = {64, (uint32_t)patch_w, (uint32_t)a.TH, 1};
+    uint32_t box[4] = {64, (uint32_t)patch_w, (uint32_t)patch_h, 1};
     int rc = make_tensor_map(&tms[i], src.ptr, p->dtype, 4, dims, str, box);
     if (rc) return rc;
   }
@@ -559,18 +645,33 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.tiles_y = ceil_div(p->H, a.TH);
   a.n_work = ceil_div(a.tiles_x * a.tiles_y * p->B, CG) * a.n_tiles;  // items of CG adjacent M tiles
   a.Cout = p->Cout; a.Cout_pad_k = p->Cout_pad_k;
-  a.a_tx_bytes = patch_w * a.TH * 128;
+  a.a_tx_bytes = patch_w * patch_h * 128;
   a.a_slot_bytes = (int)align_up((size_t)a.a_tx_bytes, 1024);
-  a.b_slot_bytes = (a.NT / CG) * 128;
+  a.b_tap_bytes = (a.NT / CG) * 128;
   {
-    // split ~212 KB between the rings: in halo mode one A patch feeds KW weight tiles, so B gets the depth
+    static const int env_group = getenv("PFB_CONV_TAP_GROUP") ? atoi(getenv("PFB_CONV_TAP_GROUP")) : 1;
+    const int taps = a.halo == 1 ? p->KW : (a.halo == 2 ? p->KH : 1);
+    a.b_group = 1;
+    // all taps of a patch in one weight stage when at least 3 such stages fit next to 3 activation patches
+    if (env_group && (taps == 3 || taps == 5) && 3 * taps * a.b_tap_bytes + 3 * a.a_slot_bytes <= 212 * 1024 && a.NT <= 192) a.b_group = taps;
+  }
+  a.b_slot_bytes = a.b_group * a.b_tap_bytes;
+  {
+    // Split ~212 KB between the rings.  The per-CTA timelines (PFB_CONV_TRACE, profiles/r01_conv_trace_*.txt) show a
+    // slot is reused only once per ~2.2 us (commit -> producer wake-up -> TMA round trip -> issue), so the number of
+    // K steps in flight, not the bytes, sets the pace of the small-N layers: maximise min(steps covered by the
+    // activation ring, weight stages).
     const int budget = 212 * 1024;
-    a.a_stages = a.halo ? 3 : 4;
-    a.b_stages = (budget - a.a_stages * a.a_slot_bytes) / a.b_slot_bytes;
-    if (a.b_stages > kMaxBStages) a.b_stages = kMaxBStages;
-    if (a.b_stages < 2) a.b_stages = 2;
-    int spare = budget - a.b_stages * a.b_slot_bytes - a.a_stages * a.a_slot_bytes;
-    while (spare >= a.a_slot_bytes && a.a_stages < kMaxAStages) { ++a.a_stages; spare -= a.a_slot_bytes; }
+    const int taps_per_patch = a.halo == 1 ? p->KW : (a.halo == 2 ? p->KH : 1);
+    int best = -1;
+    for (int as = 2; as <= kMaxAStages; ++as) {
+      int bs = (budget - as * a.a_slot_bytes) / a.b_slot_bytes;
+      if (bs > kMaxBStages) bs = kMaxBStages;
+      if (bs < 2) continue;
+      const int cover = as * taps_per_patch < bs * a.b_group ? as * taps_per_patch : bs * a.b_group;
+      if (cover > best || (cover == best && bs > a.b_stages)) { best = cover; a.a_stages = as; a.b_stages = bs; }
+    }
+    if (best < 0) return PFB_ERR_UNSUPPORTED;
   }
   a.bias = p->bias; a.epilogue = p->epilogue; a.scale = p->scale;
   a.out = p->out; a.out_stride = p->out_stride; a.out_offset = p->out_offset;
@@ -580,6 +681,28 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   int groups = sm_count() / CG;
   if (groups > a.n_work) groups = a.n_work;
   const int grid = groups * CG;
+  static const char* env_trace = getenv("PFB_CONV_TRACE");  // debug: per-CTA timeline of every launch -> JSON lines
+  if (env_trace) {
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) PFB_CUDA(cudaMalloc(&dbuf, 256 * 32 * 8));
+    PFB_CUDA(cudaMemsetAsync(dbuf, 0, 256 * 32 * 8, s));
+    a.trace = dbuf;
+    int rc;
+    if (CG == 2) rc = p->dtype == PFB_F16 ? launch_conv_umma<__half, 2>(tms, tmW, a, grid, smem, s) : launch_conv_umma<__nv_bfloat16, 2>(tms, tmW, a, grid, smem, s);
+    else rc = p->dtype == PFB_F16 ? launch_conv_umma<__half, 1>(tms, tmW, a, grid, smem, s) : launch_conv_umma<__nv_bfloat16, 1>(tms, tmW, a, grid, smem, s);
+    if (rc) return rc;
+    PFB_CUDA(cudaStreamSynchronize(s));
+    static unsigned long long host[256 * 32];
+    PFB_CUDA(cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(env_trace, "a")) {
+      fprintf(f, "{\"KH\":%d,\"KW\":%d,\"NT\":%d,\"Cin_pad\":%d,\"halo\":%d,\"TW\":%d,\"TH\":%d,\"epi\":%d,\"grid\":%d,\"n_work\":%d,\"a_stages\":%d,\"b_stages\":%d,\"b_group\":%d,\"t\":[",
+              a.KH, a.KW, a.NT, p->Cin_pad, a.halo, a.TW, a.TH, a.epilogue, grid, a.n_work, a.a_stages, a.b_stages, a.b_group);
+      for (int i = 0; i < grid * 32; ++i) fprintf(f, "%s%llu", i ? "," : "", host[i]);
+      fprintf(f, "]}\n");
+      fclose(f);
+    }
+    return PFB_OK;
+  }
   ProfScope prof(KC_CONV, s);
   if (CG == 2) {
     if (p->dtype == PFB_F16) return launch_conv_umma<__half, 2>(tms, tmW, a, grid, smem, s);

@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(LevelTable lv, const f
 template <typename T, typename TO, int R>
 __global__ void __launch_bounds__(128) corr_lookup_r4_kernel(LevelTable lv, const float* __restrict__ coords,
                                                              TO* __restrict__ out, int nq, int levels, int out_stride) {
+  pdl_wait();     // coords / volume come from the previous kernels in the stream
+  pdl_trigger();  // the next kernel may be scheduled while this grid drains
   __shared__ float smem[4][4 * 100];
   __shared__ float wts[4][4][4];
   // compile-time radius: every index division below becomes a multiply-shift
@@ -413,7 +415,7 @@ static int launch_lookup_t(const LevelTable& lv, const float* coords, void* out,
   dim3 grid(ceil_div(nq, warps));
   ProfScope prof(KC_LOOKUP, s);
   if (!nchw && (radius == 4 || radius == 3) && levels <= 4) {
-#define PFB_LOOKUP_FAST(TO, R) corr_lookup_r4_kernel<T, TO, R><<<grid, 128, 0, s>>>(lv, coords, (TO*)out, nq, levels, out_stride)
+#define PFB_LOOKUP_FAST(TO, R) launch_pdl(corr_lookup_r4_kernel<T, TO, R>, dim3(grid), dim3(128), 0, s, lv, coords, (TO*)out, nq, levels, out_stride)
     if (radius == 4) {
       if (out_dtype == PFB_F32) PFB_LOOKUP_FAST(float, 4);
       else if (out_dtype == PFB_F16) PFB_LOOKUP_FAST(__half, 4);

@@ -9,7 +9,15 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace pfb {
+
+int pdl_enabled() {
+  static const int v = getenv("PFB_PDL") ? atoi(getenv("PFB_PDL")) : 1;
+  return v;
+}
+
 
 static std::atomic<unsigned long long> g_launches[KC_COUNT];
 static std::atomic<int> g_prof_on{0};

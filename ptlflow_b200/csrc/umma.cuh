@@ -122,6 +122,12 @@ __device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* m
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
+// Same, without release semantics: for hand-offs whose only payload is TMEM access already ordered by
+// tcgen05.fence::before_thread_sync (the cluster-scope release costs a MEMBAR.ALL.GPU that waits for every
+// outstanding global store of the warp: ~0.7 us per tile in the conv epilogue, ncu source view).
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result) {  // same warp id in both CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS) : "memory");
@@ -251,6 +257,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int ab_fmt) 
   return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Warp-uniform wait: every lane polls, the loop condition is a vote (uniform predicate -> BRA.U, no divergence
+// region), so loop-carried values around it can stay in uniform registers.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_uniform(uint32_t bar_smem_addr, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait_addr(bar_smem_addr, parity))) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait_addr(bar_smem_addr, parity))) {
+    if ((++spins & 0xFF) == 0 && global_timer_ns() - t0 > PFB_MBAR_TIMEOUT_NS) __trap();
+  }
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

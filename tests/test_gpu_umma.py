@@ -101,7 +101,7 @@ def test_conv_umma_relu_linear(case, b, h, w, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("kh,kw", [(1, 5), (5, 1)])
-@pytest.mark.parametrize("h,w", [(13, 19), (6, 128)])
+@pytest.mark.parametrize("h,w", [(13, 19), (6, 128), (23, 130)])
 def test_conv_umma_gru_epilogues(dtype, kh, kw, h, w):
     """z|r fused GEMM (N = 256) + q GEMM with the gate arithmetic of update.py:58-73 in the epilogue."""
     from ptlflow_b200 import _lib, ops
