@@ -279,10 +279,12 @@ PFB_API int pfb_raft_update_iter(const pfb_raft_cfg* cfg, const pfb_raft_weights
  * The 3x3 / 7x7 / 1x1 convolutions of BasicEncoder / SmallEncoder (extractor.py:122-267) still run in
  * cuDNN; pre-processing, instance norm + ReLU (+ residual) and the residual joins are fused here.
  * ---------------------------------------------------------------------------------- */
-/* images [B,2,3,H,W] BGR in [0,1] (NCHW) -> out [2B,Hp,Wp,3] pixel-major RGB in [-1,1], replicate padded;
- * the first B entries are frame 1, the next B frame 2.     raft.py:127-135, base_model.py:206-246 */
+/* images [B,2,3,H,W] BGR in [0,1] (NCHW) -> out [2B,Hp,Wp,out_channels] pixel-major RGB in [-1,1], replicate
+ * padded; channels 3..out_channels-1 are zero (out_channels = 4 gives the first convolution 8-byte pixels, which
+ * saves cuDNN its own channel-padding pass).  The first B entries are frame 1, the next B frame 2.
+ * raft.py:127-135, base_model.py:206-246 */
 PFB_API int pfb_preprocess_frames(const void* images, void* out, int B, int H, int W, int Hp, int Wp, int pad_top,
-                                  int pad_left, pfb_dtype dtype, pfb_stream stream);
+                                  int pad_left, int out_channels, pfb_dtype dtype, pfb_stream stream);
 /* y = act(IN(x)) or, with residual, y = relu(residual + act(IN(x)));  x, y, residual: [B,H,W,C].
  * IN = nn.InstanceNorm2d defaults (no affine, biased variance, eps).   extractor.py:29-31,52-58 */
 PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C);

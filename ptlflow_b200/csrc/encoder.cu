@@ -14,8 +14,8 @@ namespace pfb {
 
 template <typename T>
 __global__ void preprocess_frames_kernel(const T* __restrict__ img, T* __restrict__ out, int B, int H, int W, int Hp,
-                                         int Wp, int pad_top, int pad_left) {
-  // out: [2B][Hp][Wp][3], frame-major (all first frames, then all second frames)
+                                         int Wp, int pad_top, int pad_left, int OC) {
+  // out: [2B][Hp][Wp][OC], frame-major (all first frames, then all second frames); channels >= 3 are zero
   const size_t total = (size_t)2 * B * Hp * Wp;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     int x = (int)(idx % Wp);
@@ -27,12 +27,13 @@ __global__ void preprocess_frames_kernel(const T* __restrict__ img, T* __restric
     sy = sy < 0 ? 0 : (sy >= H ? H - 1 : sy);
     sx = sx < 0 ? 0 : (sx >= W ? W - 1 : sx);
     const T* src = img + (((size_t)b * 2 + f) * 3) * H * W + (size_t)sy * W + sx;
-    T* o = out + idx * 3;
+    T* o = out + idx * OC;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {  // output channel c (RGB) <- input channel 2-c (BGR)
       float v = to_f32(src[(size_t)(2 - c) * H * W]);
       o[c] = from_f32<T>((v + (-0.5f)) * 2.0f);
     }
+    for (int c = 3; c < OC; ++c) o[c] = from_f32<T>(0.f);
   }
 }
 
@@ -181,8 +182,9 @@ __global__ void bias_to_ss_kernel(const float* __restrict__ bias, float2* __rest
 using namespace pfb;
 
 extern "C" PFB_API int pfb_preprocess_frames(const void* images, void* out, int B, int H, int W, int Hp, int Wp, int pad_top,
-                                             int pad_left, pfb_dtype dtype, pfb_stream stream) {
+                                             int pad_left, int out_channels, pfb_dtype dtype, pfb_stream stream) {
   PFB_CHECK_ARG(images && out, "preprocess_frames: null pointer");
+  PFB_CHECK_ARG(out_channels >= 3 && out_channels <= 16, "preprocess_frames: out_channels=%d (3..16)", out_channels);
   PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W && pad_top >= 0 && pad_left >= 0 &&
                     pad_top + H <= Hp && pad_left + W <= Wp,
                 "preprocess_frames: bad geometry %dx%d -> %dx%d (+%d,+%d)", H, W, Hp, Wp, pad_top, pad_left);
@@ -191,7 +193,7 @@ extern "C" PFB_API int pfb_preprocess_frames(const void* images, void* out, int 
   unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)sm_count() * 16);
   ProfScope prof(KC_MISC, s);
   PFB_DISPATCH_DTYPE(dtype, T, {
-    preprocess_frames_kernel<T><<<blocks, 256, 0, s>>>((const T*)images, (T*)out, B, H, W, Hp, Wp, pad_top, pad_left);
+    preprocess_frames_kernel<T><<<blocks, 256, 0, s>>>((const T*)images, (T*)out, B, H, W, Hp, Wp, pad_top, pad_left, out_channels);
   });
   PFB_LAUNCH_CHECK();
   return PFB_OK;

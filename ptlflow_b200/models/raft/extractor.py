@@ -158,7 +158,15 @@ class _Encoder(nn.Module):
                 return ops.instance_norm_act(y, relu=relu, residual=residual, out=y)
             return ops.bias_act(y, wb[1], relu=relu, residual=residual, out=y)
 
-        x = conv_act(x, prep["conv1"], 2, 3)
+        c1 = prep["conv1"]
+        if x.shape[-1] != c1[0].shape[1]:  # frames carry zero channels beyond RGB (8-byte pixels): pad the filter to match
+            key = ("conv1_pad", x.shape[-1])
+            if key not in prep:
+                w = torch.zeros((c1[0].shape[0], x.shape[-1]) + tuple(c1[0].shape[2:]), dtype=c1[0].dtype, device=c1[0].device)
+                w[:, : c1[0].shape[1]] = c1[0]
+                prep[key] = (w.contiguous(memory_format=torch.channels_last), c1[1])
+            c1 = prep[key]
+        x = conv_act(x, c1, 2, 3)
         for e in prep["blocks"]:
             s = e["stride"]
             xs = conv_act(x, e["down"], s, 0, relu=False) if "down" in e else x

@@ -62,6 +62,9 @@ class RAFT(BaseModel):
         import os as _os
         self.encoder_chunk = int(_os.environ.get("PFB_ENCODER_CHUNK", "0"))
         self.cudnn_benchmark = bool(int(_os.environ.get("PFB_CUDNN_BENCHMARK", "1")))
+        # channels of the pre-processed frames handed to the first convolution (>= 3, extra channels zero): with 3,
+        # cuDNN runs its own NHWC channel-padding kernel in front of the 7x7 convolution (ncu launch list r01 v15)
+        self.frame_channels = int(_os.environ.get("PFB_FRAME_CHANNELS", "4"))
         self._engine: Optional[RaftEngine] = None
         self._build_networks()
 
@@ -131,7 +134,7 @@ class RAFT(BaseModel):
             images = images.contiguous()
             resizer = InputPadder(images.shape, stride=self.output_stride, pad_mode="replicate", two_side_pad=True)
             B = images.shape[0]
-            frames = ops.preprocess_frames(images, resizer.tgt_size, resizer.pad_top_left)
+            frames = ops.preprocess_frames(images, resizer.tgt_size, resizer.pad_top_left, out_channels=self.frame_channels)
             fmap1, fmap2, cnet = self._encode(frames, B)
             _, H8, W8, _ = fmap1.shape
             eng = self._get_engine(fmap1.dtype, fmap1.device)

@@ -252,17 +252,18 @@ def context_split(cnet: torch.Tensor, hidden: int, context: int):
 # ------------------------------------------------------------------------------------------
 # encoder-side kernels
 # ------------------------------------------------------------------------------------------
-def preprocess_frames(images: torch.Tensor, padded_hw, pad_top_left) -> torch.Tensor:
-    """images [B,2,3,H,W] (BGR, [0,1]) -> [2B,Hp,Wp,3] pixel-major RGB in [-1,1], replicate padded; frame-major."""
+def preprocess_frames(images: torch.Tensor, padded_hw, pad_top_left, out_channels: int = 3) -> torch.Tensor:
+    """images [B,2,3,H,W] (BGR, [0,1]) -> [2B,Hp,Wp,out_channels] pixel-major RGB in [-1,1] (extra channels zero),
+    replicate padded; frame-major."""
     require_cuda(images, "images")
     B, two, three, H, W = images.shape
     if two != 2 or three != 3:
         raise RuntimeError("preprocess_frames: expected images of shape [B,2,3,H,W]")
     Hp, Wp = padded_hw
-    out = torch.empty((2 * B, Hp, Wp, 3), dtype=images.dtype, device=images.device)
+    out = torch.empty((2 * B, Hp, Wp, out_channels), dtype=images.dtype, device=images.device)
     with torch.cuda.device(images.device):
         check(load().pfb_preprocess_frames(images.data_ptr(), out.data_ptr(), B, H, W, Hp, Wp, pad_top_left[0], pad_top_left[1],
-                                           dtype_code(images.dtype), stream_ptr(images.device)), "preprocess_frames")
+                                           out_channels, dtype_code(images.dtype), stream_ptr(images.device)), "preprocess_frames")
     return out
 
 

@@ -282,6 +282,8 @@ def test_preprocess_frames_vs_oracle(h, w):
     assert out.shape == (4, ref.shape[-2], ref.shape[-1], 3)
     got = out.permute(0, 3, 1, 2).cpu()
     assert torch.equal(got[:2], ref[:, 0]) and torch.equal(got[2:], ref[:, 1])
+    out4 = ops.preprocess_frames(img.to(DEV), padder.tgt_size, padder.pad_top_left, out_channels=4)  # 8-byte pixels for conv1
+    assert out4.shape[-1] == 4 and torch.equal(out4[..., :3], out) and not out4[..., 3].any()
 
 
 @pytest.mark.parametrize("c", [64, 96, 128, 24, 8])
