@@ -290,6 +290,22 @@ PFB_API int pfb_preprocess_frames(const void* images, void* out, int B, int H, i
 PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C);
 PFB_API int pfb_instance_norm_act(const void* x, void* y, const void* residual, void* workspace, int B, int H, int W, int C,
                                   float eps, int relu, pfb_dtype dtype, pfb_stream stream);
+/* Same, for sums already accumulated into the workspace by the producing kernel (pfb_first_conv7x7s2):
+ * workspace = B*C*2 doubles (sum, sum of squares; zeroed by the caller before the producer ran) + B*C float2. */
+PFB_API int pfb_instance_norm_apply(const void* x, void* y, const void* residual, void* workspace, int B, int H, int W, int C,
+                                    float eps, int relu, pfb_dtype dtype, pfb_stream stream);
+/* First encoder convolution: nn.Conv2d(3, 64, 7, stride=2, padding=3) of BasicEncoder (extractor.py:136,171-178)
+ * on tcgen05 without an im2col buffer (overlapping-window operand descriptors, see csrc/first_conv.cu).
+ *   x      [N,H,W,4]  f16/bf16 pixel-major frames from pfb_preprocess_frames(out_channels = 4); H, W even
+ *   wpack  9 x 8192 B: for input-row offset j = 0..8 a [128][32] K-major tile, row p*64+co, column 4*t+c =
+ *          W[co][c][j-2p][t-1] (zero where j-2p or t-1 fall outside 0..6, or c = 3), stored as non-swizzled UMMA
+ *          core matrices [16 row groups][4 K groups][8 rows][8 elements]   (ptlflow_b200.ops.pack_first_conv)
+ *   bias   fp32 [64] or NULL (folded batch norm + conv bias);  relu: apply max(.,0) after the bias
+ *   stats  NULL, or B*64*2 doubles that receive per (image, channel) sum / sum of squares of the fp32 result
+ *          (instance norm: follow with pfb_instance_norm_apply)
+ *   out    [N,H/2,W/2,64] */
+PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, const float* bias, void* out, double* stats, int N, int H, int W,
+                                int relu, pfb_dtype dtype, pfb_stream stream);
 /* y = act(x + bias[c]) or, with residual, y = relu(residual + act(x + bias[c]));  bias fp32 [C] (may be NULL);
  * workspace >= 8*C bytes.  Used for the batch-norm-folded context encoder (conv bias + BN shift) and conv2. */
 PFB_API int pfb_bias_act(const void* x, const float* bias, const void* residual, void* y, void* workspace, int B, int H, int W,

@@ -236,6 +236,24 @@ extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void*
   return PFB_OK;
 }
 
+// Second half of pfb_instance_norm_act for a producer that already accumulated the sums (pfb_first_conv7x7s2):
+// workspace = [B*C*2 doubles (sum, sum of squares)] [B*C float2 scale/shift]
+extern "C" PFB_API int pfb_instance_norm_apply(const void* x, void* y, const void* residual, void* workspace, int B, int H, int W,
+                                               int C, float eps, int relu, pfb_dtype dtype, pfb_stream stream) {
+  PFB_CHECK_ARG(x && y && workspace, "instance_norm_apply: null pointer");
+  PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 512 && B <= 65535,
+                "instance_norm_apply: bad shape (C=%d must be a multiple of 8, <= 512)", C);
+  cudaStream_t s = as_stream(stream);
+  const int HW = H * W;
+  double* stats = reinterpret_cast<double*>(workspace);
+  float2* ss = reinterpret_cast<float2*>(stats + (size_t)B * C * 2);
+  ProfScope prof(KC_MISC, s);
+  inorm_finalize_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(stats, ss, B * C, HW, eps);
+  PFB_LAUNCH_CHECK();
+  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, ss, residual, y, B, HW, C, C, relu, s); });
+  return PFB_OK;
+}
+
 // y = act(x + bias[c]) [+ residual -> relu]; bias fp32 [C] or NULL; workspace >= C * 8 bytes
 extern "C" PFB_API int pfb_bias_act(const void* x, const float* bias, const void* residual, void* y, void* workspace, int B, int H,
                                     int W, int C, int relu, pfb_dtype dtype, pfb_stream stream) {

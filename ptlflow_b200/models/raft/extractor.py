@@ -3,6 +3,8 @@ cuDNN modules in channels_last; parameter names and shapes equal the reference's
 ptlflow/models/raft/extractor.py:122-267 so checkpoints load strictly)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -85,6 +87,9 @@ def _fold(conv: nn.Conv2d, norm: nn.Module, dtype, device):
     return w.to(dtype).contiguous(memory_format=torch.channels_last), b.contiguous()  # bias stays fp32: added by our kernels
 
 
+_NATIVE_CONV1 = bool(int(os.environ.get("PFB_NATIVE_CONV1", "1")))
+
+
 def _conv_pm(x: torch.Tensor, wb, stride: int, padding: int) -> torch.Tensor:
     """cuDNN convolution on a pixel-major tensor [N,H,W,C] -> [N,H',W',C'] (channels_last in and out, no copies)."""
     # no bias here: PyTorch would add it as a separate broadcast kernel; it is folded into pfb_bias_act (batch / no norm)
@@ -159,14 +164,30 @@ class _Encoder(nn.Module):
             return ops.bias_act(y, wb[1], relu=relu, residual=residual, out=y)
 
         c1 = prep["conv1"]
-        if x.shape[-1] != c1[0].shape[1]:  # frames carry zero channels beyond RGB (8-byte pixels): pad the filter to match
+        native_c1 = (_NATIVE_CONV1 and x.shape[-1] == 4 and tuple(self.conv1.weight.shape) == (64, 3, 7, 7) and x.dtype in (torch.float16, torch.bfloat16)
+                     and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0)
+        if native_c1:
+            # tcgen05 first convolution (csrc/first_conv.cu): statistics of the instance norm come out of its epilogue,
+            # bias + ReLU of the folded batch norm are applied in it
+            if "conv1_native" not in prep:
+                folded = _fold(self.conv1, self.norm1, torch.float32, x.device)
+                prep["conv1_native"] = (ops.pack_first_conv(folded[0], x.dtype), folded[1])
+            wpack, bias = prep["conv1_native"]
+            if inst:
+                ws = ops.instance_norm_workspace((x.shape[0], 0, 0, 64), x.device)
+                y = ops.first_conv7x7s2(x, wpack, None, relu=False, stats_ws=ws)
+                x = ops.instance_norm_apply(y, ws, relu=True, out=y)
+            else:
+                x = ops.first_conv7x7s2(x, wpack, bias, relu=True)
+        elif x.shape[-1] != c1[0].shape[1]:  # frames carry zero channels beyond RGB (8-byte pixels): pad the filter to match
             key = ("conv1_pad", x.shape[-1])
             if key not in prep:
                 w = torch.zeros((c1[0].shape[0], x.shape[-1]) + tuple(c1[0].shape[2:]), dtype=c1[0].dtype, device=c1[0].device)
                 w[:, : c1[0].shape[1]] = c1[0]
                 prep[key] = (w.contiguous(memory_format=torch.channels_last), c1[1])
             c1 = prep[key]
-        x = conv_act(x, c1, 2, 3)
+        if not native_c1:
+            x = conv_act(x, c1, 2, 3)
         for e in prep["blocks"]:
             s = e["stride"]
             xs = conv_act(x, e["down"], s, 0, relu=False) if "down" in e else x

@@ -291,6 +291,65 @@ def instance_norm_act(x: torch.Tensor, relu: bool = True, residual: Optional[tor
     return y
 
 
+def pack_first_conv(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """weight [64,3,7,7] (fp32, any device) -> the 9 x [128][32] operand tiles of pfb_first_conv7x7s2 (see the header):
+    row p*64+co, column 4*t+c of tile j = weight[co, c, j-2p, t-1]; non-swizzled UMMA core-matrix order."""
+    co, ci, kh, kw = weight.shape
+    if (co, ci, kh, kw) != (64, 3, 7, 7):
+        raise RuntimeError("pack_first_conv: expected a [64,3,7,7] filter")
+    w = weight.detach().float()
+    a = torch.zeros(9, 2, 64, 8, 4, dtype=torch.float32, device=w.device)  # [j][p][co][t][c]
+    for j in range(9):
+        for p in range(2):
+            ky = j - 2 * p
+            if 0 <= ky <= 6:
+                a[j, p, :, 1:8, :3] = w[:, :, ky, :].permute(0, 2, 1)  # [co][kx][c] -> t = kx + 1
+    a = a.reshape(9, 128, 32).to(dtype)
+    # [j][row group 16][row 8][K group 4][8 elements] -> [j][row group][K group][row][element]
+    return a.reshape(9, 16, 8, 4, 8).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def first_conv7x7s2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
+                    stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [N,H,W,4] f16/bf16 -> [N,H/2,W/2,64]; bias fp32 [64] or None; stats_ws: fp64 workspace whose first N*64*2
+    entries (zeroed here) receive the per-(image, channel) sums for instance_norm_apply."""
+    require_cuda(x, "x")
+    N, H, W, C4 = x.shape
+    if C4 != 4 or not x.is_contiguous():
+        raise RuntimeError("first_conv7x7s2: expected contiguous [N,H,W,4] frames")
+    out = torch.empty((N, H // 2, W // 2, 64), dtype=x.dtype, device=x.device)
+    if stats_ws is not None:
+        stats_ws[: N * 64 * 2].zero_()
+    with torch.cuda.device(x.device):
+        check(load().pfb_first_conv7x7s2(x.data_ptr(), wpack.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                         stats_ws.data_ptr() if stats_ws is not None else None, N, H, W, int(relu), dtype_code(x.dtype),
+                                         stream_ptr(x.device)), "first_conv7x7s2")
+    return out
+
+
+def instance_norm_workspace(x_shape, device) -> torch.Tensor:
+    B, _, _, Cc = x_shape
+    key = (str(device), B * Cc)
+    ws = _inorm_ws.get(key)
+    if ws is None:
+        ws = torch.empty(B * Cc * 3, dtype=torch.float64, device=device)  # sums (2 doubles) + scale/shift (2 floats)
+        _inorm_ws[key] = ws
+    return ws
+
+
+def instance_norm_apply(x: torch.Tensor, ws: torch.Tensor, relu: bool = True, residual: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(IN(x)) from sums already in ``ws`` (written by first_conv7x7s2)."""
+    require_cuda(x, "x")
+    B, H, W, Cc = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(load().pfb_instance_norm_apply(x.data_ptr(), y.data_ptr(), residual.data_ptr() if residual is not None else None,
+                                             ws.data_ptr(), B, H, W, Cc, eps, int(relu), dtype_code(x.dtype), stream_ptr(x.device)),
+              "instance_norm_apply")
+    return y
+
+
 def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True, residual: Optional[torch.Tensor] = None,
              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [B,H,W,C] -> act(x + bias[c]), or relu(residual + act(x + bias[c])).  bias: fp32 [C] or None."""

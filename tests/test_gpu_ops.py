@@ -354,3 +354,37 @@ def test_gma_attention_and_aggregate_vs_oracle(dtype, tol, h, w):
     assert attn.shape == (b * h * w, h * w)
     assert (attn.float().cpu().view(b, h * w, h * w) - attn_ref).abs().max().item() < tol
     assert (attn.float().sum(-1) - 1).abs().max().item() < (1e-5 if dtype == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 48, 64), (1, 18, 1040), (3, 20, 1024), (1, 8, 8)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["instance", "bias_relu"])
+def test_first_conv7x7s2_vs_torch(n, h, w, dtype, mode):
+    """tcgen05 first convolution (overlapping-window operand descriptors) against F.conv2d on the same rounded
+    inputs, fp32 accumulate; the instance-norm sums from its epilogue against torch sums of the fp32 result."""
+    import torch.nn.functional as F
+
+    ops = _ops()
+    wt = torch.from_numpy(synth.synth_normal("fc/w", (64, 3, 7, 7), 5, scale=0.12))
+    bias = torch.from_numpy(synth.synth_normal("fc/b", (64,), 5, scale=0.5))
+    x3 = torch.from_numpy(synth.synth_normal("fc/x", (n, h, w, 3), 6, scale=0.6)).clamp(-1, 1)
+    x4 = torch.zeros(n, h, w, 4)
+    x4[..., :3] = x3
+    xd = x4.to(DEV, dtype).contiguous()
+    wq = wt.to(dtype).float()
+    ref = F.conv2d(xd[..., :3].float().cpu().permute(0, 3, 1, 2), wq, None, stride=2, padding=3)  # [n,64,h/2,w/2]
+    wpack = ops.pack_first_conv(wt, dtype).to(DEV)
+    if mode == "instance":
+        ws = ops.instance_norm_workspace((n, 0, 0, 64), DEV)
+        out = ops.first_conv7x7s2(xd, wpack, None, relu=False, stats_ws=ws)
+        sums = ws[: n * 64 * 2].view(n, 64, 2).cpu()
+        assert torch.allclose(sums[..., 0], ref.double().sum(dim=(2, 3)), rtol=1e-3, atol=2e-2 * ref[0, 0].numel() ** 0.5)
+        assert torch.allclose(sums[..., 1], (ref.double() ** 2).sum(dim=(2, 3)), rtol=2e-3, atol=1e-2)
+    else:
+        ref = torch.relu(ref + bias.view(1, -1, 1, 1))
+        out = ops.first_conv7x7s2(xd, wpack, bias.to(DEV), relu=True)
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    tol = 6e-3 if dtype == torch.float16 else 4e-2
+    err = (got - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), f"max-abs error {err}"
