@@ -304,6 +304,16 @@ PFB_API int pfb_instance_norm_apply(const void* x, void* y, const void* residual
  *   stats  NULL, or B*64*2 doubles that receive per (image, channel) sum / sum of squares of the fp32 result
  *          (instance norm: follow with pfb_instance_norm_apply)
  *   out    [N,H/2,W/2,64] */
+/* convf1 of the motion encoder, nn.Conv2d(2, 128, 7, padding=3) + ReLU on the fp32 flow (update.py:84,96), on
+ * tcgen05 with the same overlapping-window operand (csrc/first_conv.cu).  The flow is split into hi + lo halves of
+ * the storage type inside the kernel, so the arithmetic equals fp32 flow x f16/bf16 weights, fp32 accumulate.
+ *   flow   fp32 [B,H,W,2];   bias fp32 [128]
+ *   wpack  7 x 16384 B: for filter row ky a [128][64] K-major tile, column 8*t+c = W[co][c & 1][ky][t-1] for
+ *          c < 4 (hi and lo halves see the same weight), zero for t = 0 or c >= 4; non-swizzled UMMA core-matrix
+ *          order [16 row groups][8 K groups][8 rows][8 elements]   (ptlflow_b200.ops.pack_flow_conv)
+ *   out    [B,H,W,out_stride] storage type, channels out_offset .. out_offset+127 written */
+PFB_API int pfb_flow_conv7x7(const float* flow, const void* wpack, const float* bias, void* out, int out_stride, int out_offset,
+                             int B, int H, int W, pfb_dtype dtype, pfb_stream stream);
 PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, const float* bias, void* out, double* stats, int N, int H, int W,
                                 int relu, pfb_dtype dtype, pfb_stream stream);
 /* y = act(x + bias[c]) or, with residual, y = relu(residual + act(x + bias[c]));  bias fp32 [C] (may be NULL);

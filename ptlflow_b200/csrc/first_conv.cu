@@ -245,6 +245,186 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
   if (warp == 5) tmem_dealloc<512>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// convf1 of the motion encoder: nn.Conv2d(2, 128, 7, padding=3) on the current flow (update.py:84,96), every
+// iteration.  Same overlapping-window trick with stride 1: the fp32 flow is split into hi + lo halves of the storage
+// type (fx_hi, fy_hi, fx_lo, fy_lo, 0, 0, 0, 0 = one 16-byte pixel, so no precision is lost against the fp32 SIMT
+// kernel it replaces), output pixel x reads pixels x-4 .. x+3 = 128 contiguous bytes, 16 bytes after pixel x-1's.
+// M = 128 output channels, N = 256 pixel columns (one image row segment), K = 64 per filter row, 28 MMAs per row.
+// Loader warps build the split rows in shared memory (generic stores + fence.proxy.async): no global staging buffer.
+struct FlowConvArgs {
+  const float* flow;  // [B][H][W][2]
+  const void* wpack;  // [7][16384 B]
+  const float* bias;  // [128]
+  void* out;          // [B][H][W][out_stride], channels out_offset .. out_offset + 127
+  int B, H, W, out_stride, out_offset;
+  int nseg, n_items, per_cta, ab_fmt;
+};
+constexpr int kFlRows = 7;
+constexpr int kFlSlotBytes = kFlRows * kFcRowBytes;
+constexpr int kFlABytes = 7 * 16384;
+constexpr int kFlLoaders = 128;
+
+struct __align__(8) FlBars {
+  uint64_t full[2];
+  uint64_t empty[2];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint64_t a_full;
+  uint32_t tmem_base;
+};
+
+template <typename T>
+__device__ __forceinline__ uint4 split_flow(float fx, float fy) {
+  const T hx = from_f32<T>(fx), hy = from_f32<T>(fy);
+  const T lx = from_f32<T>(fx - to_f32(hx)), ly = from_f32<T>(fy - to_f32(hy));
+  uint4 u;
+  u.x = (uint32_t)(*reinterpret_cast<const uint16_t*>(&hx)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&hy)) << 16);
+  u.y = (uint32_t)(*reinterpret_cast<const uint16_t*>(&lx)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&ly)) << 16);
+  u.z = 0u;
+  u.w = 0u;
+  return u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(448, 1) flow_conv7x7_umma_kernel(const FlowConvArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smemA = smem;
+  uint8_t* smemX = smem + kFlABytes;
+  FlBars* bars = reinterpret_cast<FlBars*>(smemX + 2 * kFlSlotBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->full[s], kFlLoaders);
+      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->acc_full[s], 1);
+      mbar_init(&bars->acc_empty[s], 8);
+    }
+    mbar_init(&bars->a_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<512>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  // the weights do not depend on the previous kernel: request them before the PDL wait
+  if (warp == 4 && lane == 0) {
+    mbar_arrive_expect_tx(&bars->a_full, kFlABytes);
+    for (int j = 0; j < 7; ++j) bulk_g2s(smemA + j * 16384, reinterpret_cast<const uint8_t*>(a.wpack) + j * 16384, 16384, &bars->a_full);
+  }
+  pdl_wait();
+  pdl_trigger();
+
+  const int w0 = blockIdx.x * a.per_cta;
+  const int w1 = min(a.n_items, w0 + a.per_cta);
+  auto decode = [&](int w, int& n, int& y, int& x0) {
+    const int row = w / a.nseg;
+    x0 = (w - row * a.nseg) * 256;
+    n = row / a.H;
+    y = row - n * a.H;
+  };
+
+  if (warp >= 10) {
+    // ================= loaders: fp32 flow rows -> split 16-byte pixels with zero halo =================
+    const int t = threadIdx.x - 320;  // 0..127
+    int i = 0;
+    for (int w = w0; w < w1; ++w, ++i) {
+      int n, y, x0;
+      decode(w, n, y, x0);
+      const int slot = i & 1;
+      mbar_wait(&bars->empty[slot], ((i >> 1) & 1) ^ 1);
+      uint8_t* base = smemX + slot * kFlSlotBytes;
+      // buffer pixel i <-> image pixel x0 - 4 + i, i in [0, 264)
+      for (int e = t; e < kFlRows * 264; e += kFlLoaders) {
+        const int j = e / 264, bi = e - j * 264;
+        const int r = y + j - 3, px = x0 - 4 + bi;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (r >= 0 && r < a.H && px >= 0 && px < a.W) {
+          const float2 f = __ldg(reinterpret_cast<const float2*>(a.flow) + ((size_t)n * a.H + r) * a.W + px);
+          u = split_flow<T>(f.x, f.y);
+        }
+        *reinterpret_cast<uint4*>(base + j * kFcRowBytes + bi * 16) = u;
+      }
+      fence_proxy_async();
+      mbar_arrive(&bars->full[slot]);
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc_f16(128, 256, a.ab_fmt);
+    const uint32_t a_hi = (1024u >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((smem_u32(smemA) & 0x3FFFF) >> 4) | ((128u >> 4) << 16);
+    mbar_wait(&bars->a_full, 0);
+    int i = 0;
+    for (int w = w0; w < w1; ++w, ++i) {
+      int n, y, x0;
+      decode(w, n, y, x0);
+      const int slot = i & 1;
+      mbar_wait(&bars->acc_empty[slot], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&bars->full[slot], (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + slot * 256;
+        const uint32_t b_lo0 = ((smem_u32(smemX + slot * kFlSlotBytes) & 0x3FFFF) >> 4) | ((16u >> 4) << 16);
+        uint32_t acc = 0;
+        for (int j = 0; j < kFlRows; ++j) {
+          if (y + j - 3 < 0 || y + j - 3 >= a.H) continue;  // rows outside the image are zero
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const uint32_t al = a_lo0 + ((j * 16384 + s * 256) >> 4);
+            const uint32_t bl = b_lo0 + ((j * kFcRowBytes + s * 32) >> 4);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                "mov.b64 da, {%1, %3};\n\t"
+                "mov.b64 db, {%2, %4};\n\t"
+                "setp.ne.b32 p, %6, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d),
+                "r"(al), "r"(bl), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(acc)
+                : "memory");
+            acc = 1;
+          }
+        }
+        umma_commit(&bars->empty[slot]);
+        umma_commit(&bars->acc_full[slot]);
+      }
+      __syncwarp();
+    }
+  } else if (warp != 4) {
+    // ================= epilogue: TMEM lane = output channel, columns = pixels =================
+    const int quarter = warp & 3, group = warp < 4 ? 0 : 1;
+    const int co = quarter * 32 + lane;
+    const float bias = a.bias ? a.bias[co] : 0.f;
+    int i = 0;
+    for (int w = w0; w < w1; ++w, ++i) {
+      int n, y, x0;
+      decode(w, n, y, x0);
+      const int slot = i & 1;
+      T* orow = reinterpret_cast<T*>(a.out) + (((size_t)n * a.H + y) * a.W) * a.out_stride + a.out_offset + co;
+      mbar_wait(&bars->acc_full[slot], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(quarter * 32) << 16);
+      for (int c = group * 32; c < 256 && x0 + c < a.W; c += 64) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        const int xb = x0 + c;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (xb + e < a.W) orow[(size_t)(xb + e) * a.out_stride] = from_f32<T>(fmaxf(__uint_as_float(r[e]) + bias, 0.f));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace pfb
 
 using namespace pfb;
@@ -278,6 +458,35 @@ extern "C" PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, con
   } else {
     PFB_CUDA(cudaFuncSetAttribute(first_conv_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFB_CUDA(launch_pdl(first_conv_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(320), smem, s, a));
+  }
+  return PFB_OK;
+}
+
+extern "C" PFB_API int pfb_flow_conv7x7(const float* flow, const void* wpack, const float* bias, void* out, int out_stride, int out_offset,
+                                        int B, int H, int W, pfb_dtype dtype, pfb_stream stream) {
+  PFB_CHECK_ARG(flow && wpack && out, "flow_conv7x7: null pointer");
+  PFB_CHECK_ARG(dtype == PFB_F16 || dtype == PFB_BF16, "flow_conv7x7: f16 / bf16 storage only");
+  PFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && out_stride >= out_offset + 128, "flow_conv7x7: bad shape");
+  PFB_CHECK_ARG((reinterpret_cast<uintptr_t>(flow) & 7) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "flow_conv7x7: alignment");
+  cudaStream_t s = as_stream(stream);
+  FlowConvArgs a{};
+  a.flow = flow; a.wpack = wpack; a.bias = bias; a.out = out;
+  a.B = B; a.H = H; a.W = W; a.out_stride = out_stride; a.out_offset = out_offset;
+  a.nseg = ceil_div(W, 256);
+  a.n_items = B * H * a.nseg;
+  int grid = sm_count();
+  if (grid > a.n_items) grid = a.n_items;
+  a.per_cta = ceil_div(a.n_items, grid);
+  grid = ceil_div(a.n_items, a.per_cta);
+  a.ab_fmt = dtype == PFB_F16 ? 0 : 1;
+  const size_t smem = kFlABytes + 2 * kFlSlotBytes + sizeof(FlBars) + 1024;
+  ProfScope prof(KC_CONV, s);
+  if (dtype == PFB_F16) {
+    PFB_CUDA(cudaFuncSetAttribute(flow_conv7x7_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFB_CUDA(launch_pdl(flow_conv7x7_umma_kernel<__half>, dim3(grid), dim3(448), smem, s, a));
+  } else {
+    PFB_CUDA(cudaFuncSetAttribute(flow_conv7x7_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFB_CUDA(launch_pdl(flow_conv7x7_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(448), smem, s, a));
   }
   return PFB_OK;
 }

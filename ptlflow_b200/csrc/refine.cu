@@ -6,6 +6,8 @@
 // the mask head + upsample run once (eval returns only the last prediction, raft.py:192).
 #include <initializer_list>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pfb {
@@ -151,7 +153,14 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
   } else {
     PFB_TRY(run_conv(x, PFB_L_CONVC1, {src_of(corr, ws.planes, corr_stride)}, PFB_EPI_RELU, corflo, ws.c_corflo, 0));
   }
-  PFB_TRY(run_conv(x, PFB_L_CONVF1, {src_of(flow, 2, 2, 0, 1)}, PFB_EPI_RELU, flo1, ws.c_flo1, 0));
+  {
+    const pfb_layer& LF = x.w->layers[PFB_L_CONVF1];
+    static const int env_fc = getenv("PFB_FLOW_CONV_UMMA") ? atoi(getenv("PFB_FLOW_CONV_UMMA")) : 1;
+    if (env_fc && LF.weight_k && LF.KH == 7 && LF.KW == 7 && LF.Cin == 2 && LF.Cout == 128 && c->dtype != PFB_F32 && c->impl != 1)
+      PFB_TRY(pfb_flow_conv7x7(flow, LF.weight_k, LF.bias, flo1, ws.c_flo1, 0, c->B, c->H, c->W, c->dtype, (pfb_stream)x.s));
+    else
+      PFB_TRY(run_conv(x, PFB_L_CONVF1, {src_of(flow, 2, 2, 0, 1)}, PFB_EPI_RELU, flo1, ws.c_flo1, 0));
+  }
   PFB_TRY(run_conv(x, PFB_L_CONVF2, {src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU, corflo, ws.c_corflo, ws.c_cor2));
   PFB_TRY(run_conv(x, PFB_L_CONV, {src_of(corflo, ws.c_corflo, ws.c_corflo)}, PFB_EPI_RELU_APPEND_FLOW, motion, ws.c_motion, 0));
 

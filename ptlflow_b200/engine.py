@@ -36,6 +36,11 @@ class RaftEngine:
 
         layers: Dict[int, ops.PackedConv] = {}
         layers[_lib.L_CONVF1] = P(None, enc.convf1)  # 7x7 on the 2-channel fp32 flow: dedicated kernel
+        if variant in (0, 2) and dtype != torch.float32 and tuple(enc.convf1.weight.shape) == (128, 2, 7, 7):
+            # tensor-core form (csrc/first_conv.cu): the K-major slot of the layer carries the overlapping-window tiles
+            pc = layers[_lib.L_CONVF1]
+            pc.weight_k = ops.pack_flow_conv(enc.convf1.weight, dtype).to(device)
+            pc.Cin_pad, pc.Cout_pad_k = 64, 128
         if variant in (0, 2):
             layers[_lib.L_CONVC1] = P([planes], enc.convc1)
             layers[_lib.L_CONVC2] = P([256], enc.convc2)

@@ -309,6 +309,30 @@ def pack_first_conv(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return a.reshape(9, 16, 8, 4, 8).permute(0, 1, 3, 2, 4).contiguous()
 
 
+def pack_flow_conv(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """weight [128,2,7,7] -> the 7 x [128][64] operand tiles of pfb_flow_conv7x7 (see the header)."""
+    if tuple(weight.shape) != (128, 2, 7, 7):
+        raise RuntimeError("pack_flow_conv: expected a [128,2,7,7] filter")
+    w = weight.detach().float()
+    a = torch.zeros(7, 128, 8, 8, dtype=torch.float32, device=w.device)  # [ky][co][t][c]
+    wk = w.permute(2, 0, 3, 1)  # [ky][co][kx][c]
+    a[:, :, 1:8, 0:2] = wk
+    a[:, :, 1:8, 2:4] = wk
+    a = a.reshape(7, 128, 64).to(dtype)
+    # [ky][row group 16][row 8][K group 8][8 elements] -> [ky][row group][K group][row][element]
+    return a.reshape(7, 16, 8, 8, 8).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def flow_conv7x7(flow: torch.Tensor, wpack: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, out_offset: int = 0) -> torch.Tensor:
+    """flow fp32 [B,H,W,2] -> out[..., out_offset:out_offset+128] = relu(conv7x7(flow) + bias)."""
+    require_cuda(flow, "flow")
+    B, H, W, _ = flow.shape
+    with torch.cuda.device(flow.device):
+        check(load().pfb_flow_conv7x7(flow.data_ptr(), wpack.data_ptr(), bias.data_ptr(), out.data_ptr(), out.shape[-1], out_offset,
+                                      B, H, W, dtype_code(out.dtype), stream_ptr(flow.device)), "flow_conv7x7")
+    return out
+
+
 def first_conv7x7s2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
                     stats_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [N,H,W,4] f16/bf16 -> [N,H/2,W/2,64]; bias fp32 [64] or None; stats_ws: fp64 workspace whose first N*64*2

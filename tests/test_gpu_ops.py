@@ -388,3 +388,23 @@ def test_first_conv7x7s2_vs_torch(n, h, w, dtype, mode):
     tol = 6e-3 if dtype == torch.float16 else 4e-2
     err = (got - ref).abs().max().item()
     assert err < tol * max(1.0, ref.abs().max().item()), f"max-abs error {err}"
+
+
+@pytest.mark.parametrize("b,h,w", [(2, 11, 21), (1, 55, 128), (1, 5, 300)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_flow_conv7x7_vs_torch(b, h, w, dtype):
+    """Tensor-core convf1 (hi/lo split of the fp32 flow) == fp32 flow x storage-type weights, fp32 accumulate."""
+    import torch.nn.functional as F
+
+    ops = _ops()
+    wt = torch.from_numpy(synth.synth_normal("fl/w", (128, 2, 7, 7), 7, scale=0.1))
+    bias = torch.from_numpy(synth.synth_normal("fl/b", (128,), 7, scale=0.3))
+    flow = torch.from_numpy(synth.synth_normal("fl/x", (b, h, w, 2), 8, scale=25.0))
+    ref = torch.relu(F.conv2d(flow.permute(0, 3, 1, 2), wt.to(dtype).float(), bias, padding=3))  # [b,128,h,w]
+    out = torch.full((b, h, w, 160), 7.0, dtype=dtype, device=DEV)
+    ops.flow_conv7x7(flow.to(DEV), ops.pack_flow_conv(wt, dtype).to(DEV), bias.to(DEV), out, out_offset=16)
+    got = out[..., 16:144].float().cpu().permute(0, 3, 1, 2)
+    assert (out[..., :16] == 7).all() and (out[..., 144:] == 7).all()
+    eps = 1e-3 if dtype == torch.float16 else 8e-3
+    err = ((got - ref).abs() / (1.0 + ref.abs())).max().item()
+    assert err < 2 * eps, f"relative error {err}"
