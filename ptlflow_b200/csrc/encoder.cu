@@ -55,7 +55,7 @@ __device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) inorm_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, int HW, int C,
+__global__ void __launch_bounds__(256) inorm_stats_kernel(const T* __restrict__ x, double* __restrict__ stats, int HW, int C,
                                                           int pix_per_block) {
   extern __shared__ float acc[];  // [2][C]
   const int b = blockIdx.y;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(512) inorm_stats_kernel(const T* __restrict__ 
   for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
   if (pl < lanes) {
     const T* base = x + (size_t)b * HW * C + 8 * co;
-#pragma unroll 8
+#pragma unroll 4
     for (int p = p0 + pl; p < p1; p += lanes) {
       float v[8];
       load8<T>(base + (size_t)p * C, v);
@@ -224,11 +224,9 @@ extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void*
   float2* ss = reinterpret_cast<float2*>(stats + (size_t)B * C * 2);
   PFB_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(double), s));
   PFB_CHECK_ARG(B <= 65535, "instance_norm_act: batch too large");
-  // ~4 blocks per SM over the whole batch (the fp64 global atomics at the end of every block serialise per address:
-  // 1760 blocks cost the 230 MB layer-1 tensors a third of their time), 512 threads with 8 loads in flight each
-  const int threads = (size_t)HW * C >= (1u << 20) ? 512 : 256;
-  int ppb = (int)(((size_t)HW * B + (size_t)4 * sm_count() - 1) / ((size_t)4 * sm_count()));
-  ppb = ppb < 64 ? 64 : (ppb > 8192 ? 8192 : ppb);
+  // plenty of blocks, few global atomics (fewer, fatter blocks were measured slower: r01 launch list v19)
+  const int threads = 256;
+  const int ppb = HW >= 8192 ? 1024 : (HW >= 1024 ? 256 : 64);
   dim3 grid(ceil_div(HW, ppb), B);
   ProfScope prof(KC_MISC, s);
   PFB_DISPATCH_DTYPE(dtype, T, { inorm_stats_kernel<T><<<grid, threads, 2 * C * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb); });

@@ -56,13 +56,34 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Epilogue store of one 32-pixel x 32-channel chunk held transposed (lane = channel, v[e] = pixel e): 2-byte global
+// stores (32 per lane, one 64-byte segment per warp instruction) made the first version store-issue bound (ncu launch
+// list r01 v18: 118 us per launch against ~25 us of MMA time).  Staged through 2 KB of warp-private shared memory
+// instead and written as 16-byte vectors: 4 stores per lane.
+template <typename T>
+__device__ __forceinline__ void store_chunk_transposed(uint8_t* stage, const float (&v)[32], T* gbase, size_t pix_stride, int npx_valid,
+                                                       int lane) {
+  T* st = reinterpret_cast<T*>(stage);
+#pragma unroll
+  for (int e = 0; e < 32; ++e) st[e * 32 + lane] = from_f32<T>(v[e]);
+  __syncwarp();
+  const int part = lane & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int px = (lane >> 2) + 8 * k;
+    if (px < npx_valid) *reinterpret_cast<uint4*>(gbase + (size_t)px * pix_stride + part * 8) = *reinterpret_cast<const uint4*>(stage + px * 64 + part * 16);
+  }
+  __syncwarp();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemX = smem + kFcABytes;
-  FcBars* bars = reinterpret_cast<FcBars*>(smemX + 2 * kFcSlotBytes);
+  uint8_t* smemStage = smemX + 2 * kFcSlotBytes;  // 8 epilogue warps x 2 KB
+  FcBars* bars = reinterpret_cast<FcBars*>(smemStage + 8 * 2048);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -193,6 +214,7 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
     const int m = quarter * 32 + lane;
     const int p = m >> 6, co = m & 63;
     const float bias = a.bias ? a.bias[co] : 0.f;
+    uint8_t* stage = smemStage + (group * 4 + quarter) * 2048;
     float ssum = 0.f, ssq = 0.f;
     int n_cur = -1;
     auto flush = [&]() {
@@ -213,7 +235,8 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
       }
       const int slot = i & 1;
       const bool row_ok = (y + p) < a.Ho;
-      T* orow = reinterpret_cast<T*>(a.out) + (((size_t)n * a.Ho + (row_ok ? y + p : 0)) * a.Wo) * 64 + co;
+      // this warp's 32 channels of the output row: channel offset (quarter & 1) * 32
+      T* orow32 = reinterpret_cast<T*>(a.out) + (((size_t)n * a.Ho + (row_ok ? y + p : 0)) * a.Wo) * 64 + (quarter & 1) * 32;
       mbar_wait(&bars->acc_full[slot], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(quarter * 32) << 16);
@@ -221,18 +244,20 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
         uint32_t r[32];
         tmem_ld_32x32(taddr + c, r);
         tmem_ld_wait();
-        if (!row_ok) continue;
         const int xb = x0 + c;
+        if (!row_ok || xb >= a.Wo) continue;  // warp-uniform
+        const int nv = a.Wo - xb;
+        float v[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          if (xb + e < a.Wo) {
-            float v = __uint_as_float(r[e]) + bias;
-            ssum += v;
-            ssq += v * v;
-            if (a.relu) v = fmaxf(v, 0.f);
-            orow[(size_t)(xb + e) * 64] = from_f32<T>(v);  // a warp writes 32 consecutive channels: one 64-byte segment
+          v[e] = __uint_as_float(r[e]) + bias;
+          if (e < nv) {
+            ssum += v[e];
+            ssq = fmaf(v[e], v[e], ssq);
           }
+          if (a.relu) v[e] = fmaxf(v[e], 0.f);
         }
+        store_chunk_transposed<T>(stage, v, orow32 + (size_t)xb * 64, 64, nv, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -293,7 +318,8 @@ __global__ void __launch_bounds__(448, 1) flow_conv7x7_umma_kernel(const FlowCon
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemX = smem + kFlABytes;
-  FlBars* bars = reinterpret_cast<FlBars*>(smemX + 2 * kFlSlotBytes);
+  uint8_t* smemStage = smemX + 2 * kFlSlotBytes;  // 8 epilogue warps x 2 KB
+  FlBars* bars = reinterpret_cast<FlBars*>(smemStage + 8 * 2048);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -397,12 +423,13 @@ __global__ void __launch_bounds__(448, 1) flow_conv7x7_umma_kernel(const FlowCon
     const int quarter = warp & 3, group = warp < 4 ? 0 : 1;
     const int co = quarter * 32 + lane;
     const float bias = a.bias ? a.bias[co] : 0.f;
+    uint8_t* stage = smemStage + (group * 4 + quarter) * 2048;
     int i = 0;
     for (int w = w0; w < w1; ++w, ++i) {
       int n, y, x0;
       decode(w, n, y, x0);
       const int slot = i & 1;
-      T* orow = reinterpret_cast<T*>(a.out) + (((size_t)n * a.H + y) * a.W) * a.out_stride + a.out_offset + co;
+      T* orow32 = reinterpret_cast<T*>(a.out) + (((size_t)n * a.H + y) * a.W) * a.out_stride + a.out_offset + quarter * 32;
       mbar_wait(&bars->acc_full[slot], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(quarter * 32) << 16);
@@ -411,9 +438,10 @@ __global__ void __launch_bounds__(448, 1) flow_conv7x7_umma_kernel(const FlowCon
         tmem_ld_32x32(taddr + c, r);
         tmem_ld_wait();
         const int xb = x0 + c;
+        float v[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (xb + e < a.W) orow[(size_t)(xb + e) * a.out_stride] = from_f32<T>(fmaxf(__uint_as_float(r[e]) + bias, 0.f));
+        for (int e = 0; e < 32; ++e) v[e] = fmaxf(__uint_as_float(r[e]) + bias, 0.f);
+        store_chunk_transposed<T>(stage, v, orow32 + (size_t)xb * a.out_stride, a.out_stride, a.W - xb, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -450,7 +478,7 @@ extern "C" PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, con
   a.ab_fmt = dtype == PFB_F16 ? 0 : 1;
   static const int env_swap = getenv("PFB_FC_DESC_SWAP") ? atoi(getenv("PFB_FC_DESC_SWAP")) : 0;
   a.swap_lbo_sbo = env_swap;
-  const size_t smem = kFcABytes + 2 * kFcSlotBytes + sizeof(FcBars) + 1024;
+  const size_t smem = kFcABytes + 2 * kFcSlotBytes + 8 * 2048 + sizeof(FcBars) + 1024;
   ProfScope prof(KC_CONV, s);
   if (dtype == PFB_F16) {
     PFB_CUDA(cudaFuncSetAttribute(first_conv_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -466,7 +494,9 @@ extern "C" PFB_API int pfb_flow_conv7x7(const float* flow, const void* wpack, co
                                         int B, int H, int W, pfb_dtype dtype, pfb_stream stream) {
   PFB_CHECK_ARG(flow && wpack && out, "flow_conv7x7: null pointer");
   PFB_CHECK_ARG(dtype == PFB_F16 || dtype == PFB_BF16, "flow_conv7x7: f16 / bf16 storage only");
-  PFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && out_stride >= out_offset + 128, "flow_conv7x7: bad shape");
+  PFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && out_stride >= out_offset + 128 && out_stride % 8 == 0 && out_offset % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "flow_conv7x7: bad shape / alignment (out_stride, out_offset multiples of 8)");
   PFB_CHECK_ARG((reinterpret_cast<uintptr_t>(flow) & 7) == 0 && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0, "flow_conv7x7: alignment");
   cudaStream_t s = as_stream(stream);
   FlowConvArgs a{};
@@ -479,7 +509,7 @@ extern "C" PFB_API int pfb_flow_conv7x7(const float* flow, const void* wpack, co
   a.per_cta = ceil_div(a.n_items, grid);
   grid = ceil_div(a.n_items, a.per_cta);
   a.ab_fmt = dtype == PFB_F16 ? 0 : 1;
-  const size_t smem = kFlABytes + 2 * kFlSlotBytes + sizeof(FlBars) + 1024;
+  const size_t smem = kFlABytes + 2 * kFlSlotBytes + 8 * 2048 + sizeof(FlBars) + 1024;
   ProfScope prof(KC_CONV, s);
   if (dtype == PFB_F16) {
     PFB_CUDA(cudaFuncSetAttribute(flow_conv7x7_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
