@@ -37,6 +37,43 @@ __global__ void preprocess_frames_kernel(const T* __restrict__ img, T* __restric
   }
 }
 
+// fast path: 4-channel output, no horizontal padding, W % 8 == 0 -> a thread turns 8 pixels (3 x 16-byte plane loads)
+// into 8 x 8-byte pixels (4 x 16-byte stores); rows are still replicate-padded vertically
+template <typename T>
+__global__ void preprocess_frames_vec8_kernel(const T* __restrict__ img, T* __restrict__ out, int B, int H, int W, int Hp, int pad_top) {
+  static_assert(sizeof(T) == 2, "16-byte vectors of 2-byte elements");
+  const int W8 = W / 8;
+  const size_t total = (size_t)2 * B * Hp * W8;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int x8 = (int)(idx % W8);
+    size_t t = idx / W8;
+    const int y = (int)(t % Hp);
+    const int n = (int)(t / Hp);
+    const int f = n / B, b = n - f * B;
+    int sy = y - pad_top;
+    sy = sy < 0 ? 0 : (sy >= H ? H - 1 : sy);
+    const T* src = img + (((size_t)b * 2 + f) * 3) * H * W + (size_t)sy * W + 8 * x8;
+    uint4 pl[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pl[c] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(2 - c) * H * W));  // RGB <- BGR planes
+    const T* r = reinterpret_cast<const T*>(&pl[0]);
+    const T* g = reinterpret_cast<const T*>(&pl[1]);
+    const T* bl = reinterpret_cast<const T*>(&pl[2]);
+    uint4 o[4];
+    T* e = reinterpret_cast<T*>(o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      e[4 * k + 0] = from_f32<T>((to_f32(r[k]) + (-0.5f)) * 2.0f);
+      e[4 * k + 1] = from_f32<T>((to_f32(g[k]) + (-0.5f)) * 2.0f);
+      e[4 * k + 2] = from_f32<T>((to_f32(bl[k]) + (-0.5f)) * 2.0f);
+      e[4 * k + 3] = from_f32<T>(0.f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (idx * 8) * 4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = o[q];
+  }
+}
+
 // ---- instance norm ---------------------------------------------------------------------------------
 // stats: [B][C][2] doubles (sum, sum of squares), zeroed by the caller-side memset node.
 // thread -> (channel octet, pixel lane): 16-byte loads, consecutive threads on consecutive octets (coalesced);
@@ -108,17 +145,6 @@ __global__ void __launch_bounds__(256) inorm_stats_kernel(const T* __restrict__ 
   }
 }
 
-// per-(sample, channel) scale / shift from the accumulated sums: y = x * rstd - mean * rstd
-__global__ void inorm_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ ss, int n, int HW, float eps) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double mean = stats[2 * i] / HW;
-  double var = stats[2 * i + 1] / HW - mean * mean;
-  var = var < 0 ? 0 : var;
-  const float rstd = rsqrtf((float)var + eps);
-  ss[i] = make_float2(rstd, (float)(-mean) * rstd);
-}
-
 // y = act(x * scale + shift)  [+ residual -> relu];  scale/shift per (sample, channel) (ss_bstride = C) or per
 // channel (ss_bstride = 0).  grid = (pixel slabs, B); a thread owns one channel octet (its 8 scale/shift pairs
 // live in registers for the whole slab) and walks pixels with 16-byte loads, four pixels in flight.
@@ -136,21 +162,36 @@ __device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
   reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// scale/shift source: the accumulated instance-norm sums (stats != null: mean / rstd recomputed per thread for its 8
+// channels -- two fp64 loads each, cheaper than a separate finalize launch), or a per-channel bias (scale 1).
 template <typename T>
-__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x, const float2* __restrict__ ss,
-                                                         const T* __restrict__ residual, T* __restrict__ y, int HW, int C,
-                                                         int ss_bstride, int relu, int pix_per_block) {
+__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x, const double* __restrict__ stats,
+                                                         const float* __restrict__ bias, const T* __restrict__ residual,
+                                                         T* __restrict__ y, int HW, int C, float eps, int relu, int pix_per_block) {
   const int b = blockIdx.y;
   const int c8n = C / 8;
   const int lanes = blockDim.x / c8n;
   const int co = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+  __shared__ float2 ss_sm[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // one fp64 mean / variance per channel and block, not per thread
+    float2 v = make_float2(1.f, bias ? __ldg(bias + c) : 0.f);
+    if (stats) {
+      const double2 sq = *reinterpret_cast<const double2*>(stats + ((size_t)b * C + c) * 2);
+      const double mean = sq.x / HW;
+      double var = sq.y / HW - mean * mean;
+      var = var < 0 ? 0 : var;
+      const float rstd = rsqrtf((float)var + eps);
+      v = make_float2(rstd, (float)(-mean) * rstd);
+    }
+    ss_sm[c] = v;
+  }
+  __syncthreads();
   if (pl >= lanes) return;
   float sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const float2 v = __ldg(ss + (size_t)b * ss_bstride + 8 * co + k);
-    sc[k] = v.x;
-    sh[k] = v.y;
+    sc[k] = ss_sm[8 * co + k].x;
+    sh[k] = ss_sm[8 * co + k].y;
   }
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, HW);
@@ -172,11 +213,6 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x
   }
 }
 
-__global__ void bias_to_ss_kernel(const float* __restrict__ bias, float2* __restrict__ ss, int C) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < C) ss[i] = make_float2(1.f, bias ? bias[i] : 0.f);
-}
-
 }  // namespace pfb
 
 using namespace pfb;
@@ -192,6 +228,14 @@ extern "C" PFB_API int pfb_preprocess_frames(const void* images, void* out, int 
   size_t total = (size_t)2 * B * Hp * Wp;
   unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)sm_count() * 16);
   ProfScope prof(KC_MISC, s);
+  if (dtype != PFB_F32 && out_channels == 4 && pad_left == 0 && Wp == W && W % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(images) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && ((size_t)H * W) % 8 == 0) {
+    blocks = (unsigned)std::min<size_t>(ceil_div_sz(total / 8, 256), (size_t)sm_count() * 16);
+    if (dtype == PFB_F16) preprocess_frames_vec8_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)images, (__half*)out, B, H, W, Hp, pad_top);
+    else preprocess_frames_vec8_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)images, (__nv_bfloat16*)out, B, H, W, Hp, pad_top);
+    PFB_LAUNCH_CHECK();
+    return PFB_OK;
+  }
   PFB_DISPATCH_DTYPE(dtype, T, {
     preprocess_frames_kernel<T><<<blocks, 256, 0, s>>>((const T*)images, (T*)out, B, H, W, Hp, Wp, pad_top, pad_left, out_channels);
   });
@@ -204,11 +248,11 @@ extern "C" PFB_API size_t pfb_instance_norm_workspace_bytes(int B, int C) {
 }
 
 template <typename T>
-static int launch_affine(const void* x, const float2* ss, const void* residual, void* y, int B, int HW, int C, int bstride, int relu,
-                         cudaStream_t s) {
+static int launch_affine(const void* x, const double* stats, const float* bias, const void* residual, void* y, int B, int HW, int C,
+                         float eps, int relu, cudaStream_t s) {
   const int ppb = HW >= 8192 ? 512 : (HW >= 1024 ? 128 : 32);
   dim3 grid(ceil_div(HW, ppb), B);
-  affine_act_kernel<T><<<grid, 256, 0, s>>>((const T*)x, ss, (const T*)residual, (T*)y, HW, C, bstride, relu, ppb);
+  affine_act_kernel<T><<<grid, 256, 0, s>>>((const T*)x, stats, bias, (const T*)residual, (T*)y, HW, C, eps, relu, ppb);
   PFB_LAUNCH_CHECK();
   return PFB_OK;
 }
@@ -221,7 +265,6 @@ extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void*
   cudaStream_t s = as_stream(stream);
   const int HW = H * W;
   double* stats = reinterpret_cast<double*>(workspace);
-  float2* ss = reinterpret_cast<float2*>(stats + (size_t)B * C * 2);
   PFB_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(double), s));
   PFB_CHECK_ARG(B <= 65535, "instance_norm_act: batch too large");
   // plenty of blocks, few global atomics (fewer, fatter blocks were measured slower: r01 launch list v19)
@@ -231,9 +274,7 @@ extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void*
   ProfScope prof(KC_MISC, s);
   PFB_DISPATCH_DTYPE(dtype, T, { inorm_stats_kernel<T><<<grid, threads, 2 * C * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb); });
   PFB_LAUNCH_CHECK();
-  inorm_finalize_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(stats, ss, B * C, HW, eps);
-  PFB_LAUNCH_CHECK();
-  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, ss, residual, y, B, HW, C, C, relu, s); });
+  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, stats, nullptr, residual, y, B, HW, C, eps, relu, s); });
   return PFB_OK;
 }
 
@@ -247,11 +288,8 @@ extern "C" PFB_API int pfb_instance_norm_apply(const void* x, void* y, const voi
   cudaStream_t s = as_stream(stream);
   const int HW = H * W;
   double* stats = reinterpret_cast<double*>(workspace);
-  float2* ss = reinterpret_cast<float2*>(stats + (size_t)B * C * 2);
   ProfScope prof(KC_MISC, s);
-  inorm_finalize_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(stats, ss, B * C, HW, eps);
-  PFB_LAUNCH_CHECK();
-  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, ss, residual, y, B, HW, C, C, relu, s); });
+  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, stats, nullptr, residual, y, B, HW, C, eps, relu, s); });
   return PFB_OK;
 }
 
@@ -259,13 +297,11 @@ extern "C" PFB_API int pfb_instance_norm_apply(const void* x, void* y, const voi
 extern "C" PFB_API int pfb_bias_act(const void* x, const float* bias, const void* residual, void* y, void* workspace, int B, int H,
                                     int W, int C, int relu, pfb_dtype dtype, pfb_stream stream) {
   PFB_CHECK_ARG(x && y && workspace, "bias_act: null pointer");
-  PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bias_act: bad shape (C=%d must be a multiple of 8)", C);
+  PFB_CHECK_ARG(dtype_ok(dtype) && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 512, "bias_act: bad shape (C=%d must be a multiple of 8, <= 512)", C);
   PFB_CHECK_ARG(B <= 65535, "bias_act: batch too large");
   cudaStream_t s = as_stream(stream);
-  float2* ss = reinterpret_cast<float2*>(workspace);
+  (void)workspace;
   ProfScope prof(KC_MISC, s);
-  bias_to_ss_kernel<<<ceil_div(C, 256), 256, 0, s>>>(bias, ss, C);
-  PFB_LAUNCH_CHECK();
-  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, ss, residual, y, B, H * W, C, 0, relu, s); });
+  PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, nullptr, bias, residual, y, B, H * W, C, 0.f, relu, s); });
   return PFB_OK;
 }

@@ -29,10 +29,11 @@ constexpr int kFcRowBytes = 4224;  // (2 * 256 + 8) pixels * 8 B = 4160, + zero 
 constexpr int kFcRows = 9;
 constexpr int kFcSlotBytes = kFcRows * kFcRowBytes;
 constexpr int kFcABytes = 9 * 8192;
+constexpr int kFcSlots = 3;
 
 struct __align__(8) FcBars {
-  uint64_t full[2];
-  uint64_t empty[2];
+  uint64_t full[kFcSlots];
+  uint64_t empty[kFcSlots];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint64_t a_full;
@@ -77,21 +78,23 @@ __device__ __forceinline__ void store_chunk_transposed(uint8_t* stage, const flo
 }
 
 template <typename T>
-__global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a) {
+__global__ void __launch_bounds__(576, 1) first_conv_umma_kernel(const FcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemX = smem + kFcABytes;
-  uint8_t* smemStage = smemX + 2 * kFcSlotBytes;  // 8 epilogue warps x 2 KB
-  FcBars* bars = reinterpret_cast<FcBars*>(smemStage + 8 * 2048);
+  uint8_t* smemStage = smemX + kFcSlots * kFcSlotBytes;  // 16 epilogue warps x 2 KB
+  FcBars* bars = reinterpret_cast<FcBars*>(smemStage + 16 * 2048);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kFcSlots; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->acc_full[s], 1);
-      mbar_init(&bars->acc_empty[s], 8);
+      mbar_init(&bars->acc_empty[s], 16);
     }
     mbar_init(&bars->a_full, 1);
     fence_barrier_init();
@@ -125,8 +128,8 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
     for (int w = w0; w < w1; ++w, ++i) {
       int n, y, x0;
       decode(w, n, y, x0);
-      const int slot = i & 1;
-      mbar_wait(&bars->empty[slot], ((i >> 1) & 1) ^ 1);
+      const int slot = i % kFcSlots;
+      mbar_wait(&bars->empty[slot], ((i / kFcSlots) & 1) ^ 1);
       uint8_t* base = smemX + slot * kFcSlotBytes;
       // pixels [plo, phi) of the row are copied to byte (plo - (2*x0 - 4)) * 8 of the row buffer; what the windows of
       // valid outputs can touch outside the image is zeroed (generic-proxy stores, fenced before the hand-off)
@@ -177,12 +180,12 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
     for (int w = w0; w < w1; ++w, ++i) {
       int n, y, x0;
       decode(w, n, y, x0);
-      const int slot = i & 1;
-      mbar_wait(&bars->acc_empty[slot], ((i >> 1) & 1) ^ 1);
-      mbar_wait(&bars->full[slot], (i >> 1) & 1);
+      const int slot = i % kFcSlots, acc_slot = i & 1;  // 3 input-row slots in flight (one was load-latency bound), 2 accumulators
+      mbar_wait(&bars->acc_empty[acc_slot], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&bars->full[slot], (i / kFcSlots) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d = tmem_base + slot * 256;
+        const uint32_t d = tmem_base + acc_slot * 256;
         const uint32_t b_lo0 = ((smem_u32(smemX + slot * kFcSlotBytes) & 0x3FFFF) >> 4) | (b_lbo << 16);
         const int r0 = 2 * y - 3;
         uint32_t acc = 0;
@@ -204,13 +207,17 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
           }
         }
         umma_commit(&bars->empty[slot]);
-        umma_commit(&bars->acc_full[slot]);
+        umma_commit(&bars->acc_full[acc_slot]);
       }
       __syncwarp();
     }
   } else {
     // ================= epilogue: TMEM lane = (row phase p, channel co), columns = pixels =================
-    const int quarter = warp & 3, group = warp < 4 ? 0 : 1;
+    // 16 epilogue warps (0-3, 6-17): four column groups x four TMEM lane quarters (a warp may only touch quarter
+    // warp % 4).  Each warp owns two 32-pixel chunks of an item; both TMEM loads are issued together and the
+    // accumulator is handed back to the MMA warp as soon as they have landed in registers -- the per-warp chain
+    // load -> arithmetic -> stores was what bounded the 8-warp version (90 us for 16 frames against 30 us of MMA).
+    const int quarter = warp & 3, group = warp < 4 ? 0 : 1 + ((warp - 6) >> 2);
     const int m = quarter * 32 + lane;
     const int p = m >> 6, co = m & 63;
     const float bias = a.bias ? a.bias[co] : 0.f;
@@ -240,17 +247,22 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
       mbar_wait(&bars->acc_full[slot], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + slot * 256 + ((uint32_t)(quarter * 32) << 16);
-      for (int c = group * 32; c < 256; c += 64) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        const int xb = x0 + c;
+      uint32_t r[2][32];
+      tmem_ld_32x32(taddr + group * 32, r[0]);
+      tmem_ld_32x32(taddr + group * 32 + 128, r[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int xb = x0 + group * 32 + 128 * k;
         if (!row_ok || xb >= a.Wo) continue;  // warp-uniform
         const int nv = a.Wo - xb;
         float v[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          v[e] = __uint_as_float(r[e]) + bias;
+          v[e] = __uint_as_float(r[k][e]) + bias;
           if (e < nv) {
             ssum += v[e];
             ssq = fmaf(v[e], v[e], ssq);
@@ -259,9 +271,6 @@ __global__ void __launch_bounds__(320, 1) first_conv_umma_kernel(const FcArgs a)
         }
         store_chunk_transposed<T>(stage, v, orow32 + (size_t)xb * 64, 64, nv, lane);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[slot]);
     }
     flush();
   }
@@ -478,14 +487,14 @@ extern "C" PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, con
   a.ab_fmt = dtype == PFB_F16 ? 0 : 1;
   static const int env_swap = getenv("PFB_FC_DESC_SWAP") ? atoi(getenv("PFB_FC_DESC_SWAP")) : 0;
   a.swap_lbo_sbo = env_swap;
-  const size_t smem = kFcABytes + 2 * kFcSlotBytes + 8 * 2048 + sizeof(FcBars) + 1024;
+  const size_t smem = kFcABytes + kFcSlots * kFcSlotBytes + 16 * 2048 + sizeof(FcBars) + 1024;
   ProfScope prof(KC_CONV, s);
   if (dtype == PFB_F16) {
     PFB_CUDA(cudaFuncSetAttribute(first_conv_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PFB_CUDA(launch_pdl(first_conv_umma_kernel<__half>, dim3(grid), dim3(320), smem, s, a));
+    PFB_CUDA(launch_pdl(first_conv_umma_kernel<__half>, dim3(grid), dim3(576), smem, s, a));
   } else {
     PFB_CUDA(cudaFuncSetAttribute(first_conv_umma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PFB_CUDA(launch_pdl(first_conv_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(320), smem, s, a));
+    PFB_CUDA(launch_pdl(first_conv_umma_kernel<__nv_bfloat16>, dim3(grid), dim3(576), smem, s, a));
   }
   return PFB_OK;
 }
