@@ -596,7 +596,9 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   static const int env_desc = getenv("PFB_UMMA_DESC_MODE") ? atoi(getenv("PFB_UMMA_DESC_MODE")) : 0;
   static const int env_vhalo = getenv("PFB_CONV_VHALO") ? atoi(getenv("PFB_CONV_VHALO")) : 1;
   a.halo = (env_halo && a.TH == 1 && p->KW > 1) ? 1 : 0;
-  if (env_vhalo && p->KW == 1 && p->KH > 1) {
+  // (with all 256 output channels in one tile the 448-tile grid of the 8x16 patches costs a fourth round that the
+  //  smaller activation traffic does not pay back: 61.5 vs 57.8 us on the z|r layer, launch lists v13-v15)
+  if (env_vhalo && p->KW == 1 && p->KH > 1 && p->Cout_pad_k / ceil_div(p->Cout_pad_k, 256) < 256) {
     // vertical taps: a (TH + KH - 1) x TW patch serves all KH taps of a chunk when the per-tap offset TW * 128 B keeps
     // the 1024-byte swizzle phase (TW % 8 == 0).  Fewest tiles first, then the smallest patch.
     long best_tiles = -1, best_patch = 0;

@@ -488,7 +488,7 @@ extern "C" PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, con
   static const int env_swap = getenv("PFB_FC_DESC_SWAP") ? atoi(getenv("PFB_FC_DESC_SWAP")) : 0;
   a.swap_lbo_sbo = env_swap;
   const size_t smem = kFcABytes + kFcSlots * kFcSlotBytes + 16 * 2048 + sizeof(FcBars) + 1024;
-  ProfScope prof(KC_CONV, s);
+  ProfScope prof(KC_MISC, s);  // encoder side: not part of the update-block conv roofline
   if (dtype == PFB_F16) {
     PFB_CUDA(cudaFuncSetAttribute(first_conv_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFB_CUDA(launch_pdl(first_conv_umma_kernel<__half>, dim3(grid), dim3(576), smem, s, a));
