@@ -106,15 +106,20 @@ class RaftEngine:
                             self.impl)
 
     def workspace(self, cfg: _lib.RaftCfg) -> torch.Tensor:
+        # one workspace per CUDA stream (batches in flight on different streams must not share scratch memory,
+        # ptlflow_b200/pipeline.py) and, per stream, one shape resident (bounded memory)
+        sid = torch.cuda.current_stream(self.device).cuda_stream
         key = (cfg.B, cfg.H, cfg.W)
-        ws = self._workspaces.get(key)
-        if ws is None:
+        ent = self._workspaces.get(sid)
+        if ent is None or ent[0] != key:
             nbytes = load().pfb_raft_workspace_bytes(C.byref(cfg))
             if nbytes == 0:
                 check(-1, "raft_workspace_bytes")
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._workspaces = {key: ws}  # keep one shape resident (bounded memory)
-        return ws
+            ent = (key, torch.empty(nbytes, dtype=torch.uint8, device=self.device))
+            if len(self._workspaces) >= 8:  # streams come and go: do not grow without bound
+                self._workspaces.pop(next(iter(self._workspaces)))
+            self._workspaces[sid] = ent
+        return ent[1]
 
     def refine(self, pyramid: Sequence[torch.Tensor], net: torch.Tensor, inp: torch.Tensor, coords: torch.Tensor,
                iters: int, out_hw, pad, fmap1: Optional[torch.Tensor] = None, attention: Optional[torch.Tensor] = None):

@@ -11,6 +11,9 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import contextlib
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -20,6 +23,32 @@ from ...utils.registry import ptlflow_trained, register_model, trainable
 from ..base_model.base_model import BaseModel
 from .extractor import BasicEncoder, SmallEncoder
 from .update import BasicUpdateBlock, SmallUpdateBlock
+
+
+_cudnn_lock = threading.Lock()
+_cudnn_users = 0
+_cudnn_saved = None
+
+
+@contextlib.contextmanager
+def _cudnn_flags(benchmark: bool, allow_tf32: bool):
+    """torch.backends.cudnn.flags() saves / restores process-global flags; with several forwards in flight on
+    different host threads (pipeline.FramePipeline) the first to leave would switch benchmark mode off under the
+    others.  First in sets, last out restores."""
+    global _cudnn_users, _cudnn_saved
+    cd = torch.backends.cudnn
+    with _cudnn_lock:
+        if _cudnn_users == 0:
+            _cudnn_saved = (cd.enabled, cd.benchmark, cd.allow_tf32)
+            cd.enabled, cd.benchmark, cd.allow_tf32 = True, benchmark, allow_tf32
+        _cudnn_users += 1
+    try:
+        yield
+    finally:
+        with _cudnn_lock:
+            _cudnn_users -= 1
+            if _cudnn_users == 0:
+                cd.enabled, cd.benchmark, cd.allow_tf32 = _cudnn_saved
 
 
 class SequenceLoss(nn.Module):
@@ -114,7 +143,7 @@ class RAFT(BaseModel):
         # cuDNN autotuning: its heuristics pick an fp32 SIMT kernel for the strided 96->128 convolutions of layer3
         # (ncu launch list r01_launches_v7); benchmark mode selects per shape once.
         strict = frames.dtype == torch.float32 and self.strict_fp32
-        with torch.backends.cudnn.flags(enabled=True, benchmark=self.cudnn_benchmark, allow_tf32=not strict):
+        with _cudnn_flags(self.cudnn_benchmark, not strict):
             fmaps = run(self.fnet, frames)
             cnet = run(self.cnet, frames[:B])
         return fmaps[:B], fmaps[B:], cnet

@@ -276,7 +276,7 @@ def instance_norm_act(x: torch.Tensor, relu: bool = True, residual: Optional[tor
     require_cuda(x, "x")
     B, H, W, Cc = x.shape
     y = out if out is not None else torch.empty_like(x)
-    key = (str(x.device), B * Cc)
+    key = (str(x.device), B * Cc, torch.cuda.current_stream(x.device).cuda_stream)  # scratch is per stream
     ws = _inorm_ws.get(key)
     if ws is None:
         ws = torch.empty(B * Cc * 3, dtype=torch.float64, device=x.device)  # sums (2 doubles) + scale/shift (2 floats)
@@ -353,7 +353,7 @@ def first_conv7x7s2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.T
 
 def instance_norm_workspace(x_shape, device) -> torch.Tensor:
     B, _, _, Cc = x_shape
-    key = (str(device), B * Cc)
+    key = (str(device), B * Cc, torch.cuda.current_stream(device).cuda_stream)  # scratch is per stream
     ws = _inorm_ws.get(key)
     if ws is None:
         ws = torch.empty(B * Cc * 3, dtype=torch.float64, device=device)  # sums (2 doubles) + scale/shift (2 floats)
@@ -380,7 +380,7 @@ def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True, r
     require_cuda(x, "x")
     B, H, W, Cc = x.shape
     y = out if out is not None else torch.empty_like(x)
-    key = (str(x.device), "bias", Cc)
+    key = (str(x.device), "bias", Cc, torch.cuda.current_stream(x.device).cuda_stream)
     ws = _inorm_ws.get(key)
     if ws is None:
         ws = torch.empty(Cc, dtype=torch.float64, device=x.device)

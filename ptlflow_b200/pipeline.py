@@ -1,0 +1,132 @@
+"""FramePipeline: several frame-pair batches in flight on one GPU.
+
+One forward of a RAFT-family model is a chain of ~250 dependent kernels that alternate between tensor-bound
+(update-block convolutions), HBM-bound (encoder normalisation passes, lookup, volume) and latency-bound phases.
+Two independent batches on two CUDA streams fill each other's gaps: measured on B200, RAFT 1024x436 / 12 iterations
+/ f16 / 8 pairs per batch, 818 -> 894 pairs/s with two batches in flight (three bring nothing more).
+
+Each slot owns a CUDA stream, a host thread (kernel launches of one forward take ~6 ms of host time; cuDNN's
+autotune cache in torch is thread-local, so the thread is long-lived and warms up once) and, through the
+stream-keyed scratch caches of ``ptlflow_b200.engine`` / ``ptlflow_b200.ops``, its own workspaces.  Weights and
+packed filters are shared read-only.  Results are bit-identical to sequential calls
+(``tests/test_gpu_e2e.py::test_pipeline_matches_sequential``).
+
+This is host plumbing around ``model(inputs)``; it has no counterpart in the reference, whose ``infer.py`` /
+``validate.py`` loops call the model one batch at a time.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from concurrent.futures import Future
+from typing import Dict, List, Optional
+
+import torch
+
+
+class _Result:
+    """Outputs of one submitted batch; ``get()`` waits for the slot's stream to reach the end of that batch."""
+
+    def __init__(self, future: Future):
+        self._future = future
+
+    def get(self) -> Dict[str, torch.Tensor]:
+        out, event = self._future.result()
+        event.synchronize()
+        cur = torch.cuda.current_stream()
+        for v in out.values():  # allocated on the slot's stream, consumed on the caller's
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(cur)
+        return out
+
+    def enqueued(self) -> None:
+        """Returns when the host side has finished launching the batch (the GPU may still be running it)."""
+        self._future.result()
+
+
+class FramePipeline:
+    def __init__(self, model: torch.nn.Module, depth: int = 2, device: Optional[torch.device] = None):
+        if depth < 1:
+            raise ValueError("FramePipeline: depth must be >= 1")
+        self.model = model
+        self.device = device if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("FramePipeline needs a model on a CUDA device")
+        self.depth = depth
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+        self._queues: List[queue.Queue] = [queue.Queue() for _ in range(depth)]
+        self._dev_in: List[Optional[torch.Tensor]] = [None] * depth
+        self._next = 0
+        self._pending: List[_Result] = []
+        self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True, name=f"pfb-slot{i}") for i in range(depth)]
+        for t in self._threads:
+            t.start()
+
+    # -- worker ------------------------------------------------------------------------------
+    def _run(self, slot: int) -> None:
+        torch.cuda.set_device(self.device)
+        stream = self.streams[slot]
+        q = self._queues[slot]
+        with torch.no_grad(), torch.cuda.stream(stream):
+            while True:
+                job = q.get()
+                if job is None:
+                    return
+                images, extra, host_out, ready, fut = job
+                try:
+                    stream.wait_event(ready)  # everything the caller had enqueued before submit()
+                    if not images.is_cuda:  # pinned host frames: H2D on this slot's stream, overlapping the other slot's compute
+                        buf = self._dev_in[slot]
+                        if buf is None or buf.shape != images.shape or buf.dtype != images.dtype:
+                            buf = torch.empty(images.shape, dtype=images.dtype, device=self.device)
+                            self._dev_in[slot] = buf
+                        buf.copy_(images, non_blocking=True)
+                        images = buf
+                    inputs = dict(extra)
+                    inputs["images"] = images
+                    out = self.model(inputs)
+                    if host_out is not None:
+                        host_out.copy_(out["flows"], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(stream)
+                    fut.set_result((out, done))
+                except BaseException as e:  # noqa: BLE001 -- delivered to the caller through the future
+                    fut.set_exception(e)
+
+    # -- caller side ---------------------------------------------------------------------------
+    def submit(self, inputs: Dict[str, torch.Tensor], host_out: Optional[torch.Tensor] = None) -> _Result:
+        """Enqueue ``model(inputs)`` on the next slot.  ``inputs["images"]`` may live on the device or in (pinned) host
+        memory; with ``host_out`` (pinned, shape of ``flows``) the predicted flow is copied back on the slot's stream."""
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        fut: Future = Future()
+        extra = {k: v for k, v in inputs.items() if k != "images"}
+        self._queues[slot].put((inputs["images"], extra, host_out, ready, fut))
+        res = _Result(fut)
+        self._pending.append(res)
+        return res
+
+    def drain(self) -> None:
+        """Host: wait until every submitted batch has been launched; device: make the caller's current stream wait for
+        all slots (so an event recorded after drain() brackets the submitted work)."""
+        for r in self._pending:
+            r.enqueued()
+        self._pending.clear()
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def close(self) -> None:
+        for q in self._queues:
+            q.put(None)
+        for t in self._threads:
+            t.join(timeout=60)
+
+    def __enter__(self) -> "FramePipeline":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.drain()
+        self.close()
