@@ -208,6 +208,10 @@ PFB_API int pfb_context_split(const void* cnet, void* net, void* inp, int B, int
                       pfb_dtype dtype, pfb_stream stream);
 /* coords[b,y,x] = (x, y) + (flow_init ? flow_init[b,:,y,x] (NCHW fp32) : 0)   raft.py:103-110,162-167 */
 PFB_API int pfb_init_coords(float* coords, const float* flow_init_nchw, int B, int H, int W, pfb_stream stream);
+/* Warm start: forward_interpolate of ptlflow/utils/external/raft.py:155-185 /
+ * ptlflow/utils/utils.py:454-478 (scipy griddata(method="nearest") on the CPU there) on the device.
+ * flow_nchw, out_nchw: fp32 [B,2,H,W]; exact nearest neighbour in fp64, ties to the lowest source index. */
+PFB_API int pfb_forward_interpolate(const float* flow_nchw, float* out_nchw, int B, int H, int W, pfb_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * a6-a9, a11: the refinement loop   (BasicUpdateBlock / SmallUpdateBlock + RAFT.forward loop)

@@ -100,6 +100,7 @@ SIGNATURES = {
     "pfb_flow_tap_gather": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _S]),
     "pfb_context_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_init_coords": (_I, [_P, _P, _I, _I, _I, _S]),
+    "pfb_forward_interpolate": (_I, [_P, _P, _I, _I, _I, _S]),
     "pfb_raft_workspace_bytes": (C.c_size_t, [C.POINTER(RaftCfg)]),
     "pfb_raft_refine": (_I, [C.POINTER(RaftCfg), C.POINTER(RaftWeights), C.POINTER(RaftBuffers), _S]),
     "pfb_preprocess_frames": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S]),

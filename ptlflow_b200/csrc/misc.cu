@@ -87,6 +87,49 @@ __global__ void context_split_vec8_kernel(const T* __restrict__ cnet, T* __restr
   }
 }
 
+// Warm start: RAFT's forward_interpolate (ptlflow/utils/external/raft.py:155-185, scipy griddata(method="nearest") on
+// the CPU in the reference): every pixel of the previous flow is pushed to (x + dx, y + dy); points that land strictly
+// inside the image are kept; each grid pixel takes the flow of its nearest kept point.  Brute force, N^2 distance
+// evaluations per sample in fp64 (the reference's points are float64 = integer grid + float32 flow, exact here too);
+// ties go to the lowest source index.
+__global__ void __launch_bounds__(128) forward_interpolate_kernel(const float* __restrict__ flow, float* __restrict__ out, int H, int W) {
+  __shared__ double2 pts[256];
+  const int N = H * W, b = blockIdx.y;
+  const float* fx = flow + (size_t)b * 2 * N;
+  const float* fy = fx + N;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const double qx = (double)(q % W), qy = (double)(q / W);
+  double best = 1e300;
+  int best_i = -1;
+  for (int p0 = 0; p0 < N; p0 += 256) {
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+      const int p = p0 + t;
+      double2 v = make_double2(1e150, 1e150);  // never the nearest
+      if (p < N) {
+        const double x1 = (double)(p % W) + (double)fx[p], y1 = (double)(p / W) + (double)fy[p];
+        if (x1 > 0.0 && x1 < (double)W && y1 > 0.0 && y1 < (double)H) v = make_double2(x1, y1);
+      }
+      pts[t] = v;
+    }
+    __syncthreads();
+    const int n = min(256, N - p0);
+    for (int t = 0; t < n; ++t) {
+      const double ddx = pts[t].x - qx, ddy = pts[t].y - qy;
+      const double d = ddx * ddx + ddy * ddy;
+      if (d < best) {
+        best = d;
+        best_i = p0 + t;
+      }
+    }
+    __syncthreads();
+  }
+  if (q < N) {
+    const bool ok = best_i >= 0 && best < 1e290;
+    out[(size_t)b * 2 * N + q] = ok ? fx[best_i] : 0.f;
+    out[(size_t)b * 2 * N + N + q] = ok ? fy[best_i] : 0.f;
+  }
+}
+
 __global__ void init_coords_kernel(float* __restrict__ coords, const float* __restrict__ flow_init, int B, int H,
                                    int W) {
   const int P = B * H * W;
@@ -295,6 +338,14 @@ extern "C" PFB_API int pfb_context_split(const void* cnet, void* net, void* inp,
       context_split_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>((const T*)cnet, (T*)net, (T*)inp, P, hidden, context);
     });
   }
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}
+
+extern "C" PFB_API int pfb_forward_interpolate(const float* flow_nchw, float* out_nchw, int B, int H, int W, pfb_stream stream) {
+  PFB_CHECK_ARG(flow_nchw && out_nchw && B > 0 && H > 0 && W > 0 && B <= 65535, "forward_interpolate: bad arguments");
+  ProfScope prof(KC_MISC, as_stream(stream));
+  forward_interpolate_kernel<<<dim3(ceil_div(H * W, 128), B), 128, 0, as_stream(stream)>>>(flow_nchw, out_nchw, H, W);
   PFB_LAUNCH_CHECK();
   return PFB_OK;
 }

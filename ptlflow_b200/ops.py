@@ -236,6 +236,19 @@ def init_coords(B: int, H: int, W: int, device, flow_init: Optional[torch.Tensor
     return coords
 
 
+def forward_interpolate(flow: torch.Tensor) -> torch.Tensor:
+    """flow [B,2,H,W] on CUDA -> forward-warped, nearest-filled flow [B,2,H,W] fp32 (warm start)."""
+    require_cuda(flow, "flow")
+    f = flow.detach().to(torch.float32).contiguous()
+    B, two, H, W = f.shape
+    if two != 2:
+        raise RuntimeError("forward_interpolate: expected [B,2,H,W]")
+    out = torch.empty_like(f)
+    with torch.cuda.device(f.device):
+        check(load().pfb_forward_interpolate(f.data_ptr(), out.data_ptr(), B, H, W, stream_ptr(f.device)), "forward_interpolate")
+    return out
+
+
 def context_split(cnet: torch.Tensor, hidden: int, context: int):
     """cnet [B,H,W,hidden+context] -> (tanh(net), relu(inp)) pixel-major.  raft.py:155-158."""
     require_cuda(cnet, "cnet")

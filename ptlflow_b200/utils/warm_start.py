@@ -1,9 +1,10 @@
 """Warm start: forward-warp the previous low-resolution flow (RAFT's ``forward_interpolate``).
 
 The reference does this on the CPU with scipy ``griddata(method="nearest")``
-(ptlflow/utils/external/raft.py:155-185, wrapper ptlflow/utils/utils.py:454-478); it is only used
-with ``warm_start=True`` and is marked out of scope for the hot path.  Kept
-as host plumbing with the same semantics so ``prev_preds`` round-trips.
+(ptlflow/utils/external/raft.py:155-185, wrapper ptlflow/utils/utils.py:454-478), on the critical path of
+``infer.py`` / ``validate.py`` when ``warm_start=True``.  CUDA tensors go through
+``pfb_forward_interpolate`` (exact nearest neighbour in fp64 on the device, no host round trip); the scipy form
+below is the restatement of the reference for host tensors and the checker of the device kernel in the tests.
 """
 from __future__ import annotations
 
@@ -30,5 +31,9 @@ def _forward_interpolate(flow: torch.Tensor) -> torch.Tensor:
 
 
 def forward_interpolate_batch(prev_flow: torch.Tensor) -> torch.Tensor:
+    if prev_flow.is_cuda:
+        from .. import ops
+
+        return ops.forward_interpolate(prev_flow).to(dtype=prev_flow.dtype)
     out = torch.stack([_forward_interpolate(prev_flow[i]) for i in range(prev_flow.shape[0])], dim=0)
     return out.to(dtype=prev_flow.dtype, device=prev_flow.device)

@@ -408,3 +408,18 @@ def test_flow_conv7x7_vs_torch(b, h, w, dtype):
     eps = 1e-3 if dtype == torch.float16 else 8e-3
     err = ((got - ref).abs() / (1.0 + ref.abs())).max().item()
     assert err < 2 * eps, f"relative error {err}"
+
+
+@pytest.mark.parametrize("b,h,w,scale", [(2, 16, 24, 3.0), (1, 55, 128, 8.0), (1, 9, 11, 40.0)])
+def test_forward_interpolate_vs_scipy(b, h, w, scale):
+    """Device warm start == the reference's scipy griddata(nearest) forward_interpolate (utils/external/raft.py:155-185);
+    the only admissible differences are exact distance ties."""
+    from ptlflow_b200.utils.warm_start import forward_interpolate_batch
+
+    flow = torch.from_numpy(synth.synth_normal("fi/flow", (b, 2, h, w), 9, scale=scale))
+    ref = forward_interpolate_batch(flow)  # host tensors: scipy restatement of the reference
+    got = forward_interpolate_batch(flow.to(DEV)).cpu()
+    assert got.shape == ref.shape
+    mismatch = ((got - ref).abs().amax(dim=1) > 0).float().mean().item()
+    assert mismatch < 2e-3, f"{mismatch:.4f} of the pixels differ from scipy's nearest neighbour"
+    assert torch.equal(forward_interpolate_batch(torch.full((1, 2, 6, 7), 1000.0, device=DEV)).cpu(), torch.zeros(1, 2, 6, 7))  # nothing lands inside

@@ -1,4 +1,13 @@
-timeout 200 python tools/time_config.py --model gma --batch 4 --height 436 --width 1024 --iters 12 --dtype bf16 --steps 6 | tee gpurun_out/cfg3_gma_v22.json
-timeout 200 python tools/time_config.py --model raft --batch 1 --height 1080 --width 1920 --iters 32 --dtype fp16 --steps 4 | tee gpurun_out/cfg4_vol_v22.json
-timeout 300 python tools/time_config.py --model raft --batch 1 --height 1080 --width 1920 --iters 32 --dtype fp16 --steps 3 --alternate-corr | tee gpurun_out/cfg4_alt_v22.json
-timeout 200 python tools/time_config.py --model raft_small --batch 1 --height 128 --width 256 --iters 4 --dtype fp32 --steps 20 | tee gpurun_out/cfg1_small_v22.json
+timeout 300 python -m pytest tests/test_gpu_ops.py tests/test_gpu_e2e.py -m gpu -x -q -k "forward_interpolate or warm_start or pipeline" 2>&1 | tail -3
+for P in 1024 768 1536 512; do
+PFB_STATS_PPB=$P timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -k regex:inorm_stats --csv --log-file gpurun_out/stats_ppb$P.csv python tools/profile_step.py --iters 1 > /dev/null 2>&1
+python - <<PY
+import csv
+rows=list(csv.reader(open('gpurun_out/stats_ppb$P.csv')))
+h=[i for i,r in enumerate(rows) if 'Kernel Name' in r][0]
+mv=rows[h].index('Metric Value')
+v=[float(r[mv].replace(',','')) for r in rows[h+1:] if len(r)>mv]
+v=[x/1000 if x>1000 else x for x in v]
+print('ppb',$P,'sum us',round(sum(v),1),[round(x,1) for x in v])
+PY
+done
