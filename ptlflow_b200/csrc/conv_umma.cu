@@ -2,21 +2,28 @@
 //
 //   out[p, n] = epilogue( bias[n] + sum_{tap, src, c} X_src[p + tap, c] * Wk[tap][n][kpos(src, c)] )
 //
-//   M tile : 128 pixels = an 8-row x 16-col patch of one image.  The A operand of tap (dy, dx) is ONE
-//            TMA box of the pixel-major activation tensor at coordinates (c0, x0+dx, y0+dy, b): out-of-image
-//            elements are zero-filled by the TMA unit, which is exactly "same" zero padding -- no im2col,
-//            no halo logic, no torch.cat (each concatenated source has its own tensor map).
+//   M tile : 128 pixels = TW x TH of one image, chosen per shape for the least padding (one image row, 128 x 1, for
+//            W = 128: 440 tiles = 2.97 waves of 148 SMs).  The A operand of a tap is a TMA box of the pixel-major
+//            activation tensor: out-of-image elements are zero-filled by the TMA unit, which is exactly "same"
+//            zero padding -- no im2col, no torch.cat (each concatenated source has its own tensor map).
+//            Halo reuse: with row tiles one patch of TW + KW - 1 pixels serves all KW horizontal taps (tap kx =
+//            the same patch read through a descriptor advanced by kx * 128 B); vertical kernels with N < 256 use
+//            (TH + KH - 1) x TW patches the same way (advance TW * 128 B, a multiple of the 1024-byte swizzle period).
 //   N tile : all (<= 256) output channels of the layer in one TMEM accumulator (z|r of the GRU = 256).
-//   K loop : (tap, source, 64-channel chunk); one pipeline stage = A box (16 KB) + weight tile (N x 128 B).
+//   K loop : (64-channel chunk of a source, ky, kx).  Two rings: activation patches and weight tiles; a weight stage
+//            holds one tap (N = 256) or all taps of a patch (N <= 192, "b_group").
+//   CG = 2 : CTA pairs (cta_group::2): the pair shares every weight tile, the leader issues M = 256 MMAs.
 //
 // Persistent CTAs (one per SM, 10 warps: 4 = TMA producer, 5 = MMA issuer / TMEM owner, 0-3 and 6-9 = two
-// epilogue groups that split the accumulator columns between them) walk the
-// output tiles round-robin.  The smem ring (4-8 stages, ~200 KB) runs continuously across tiles and the
-// accumulator is double-buffered in TMEM (2 x <=256 columns), so the epilogue of tile i overlaps the MMAs of
-// tile i+1 and the TMA producer never drains at a tile boundary.  The 128-pixel M tile is TW x TH with TW*TH = 128
-// chosen per shape to minimise padding (128x1 rows for W = 128: 440 tiles = 2.97 waves of 148 SMs).
-// The epilogue fuses bias + ReLU / sigmoid / tanh + the GRU gate arithmetic of
-// ptlflow/models/raft/update.py:58-73 and writes pixel-major f16/bf16 with 16-byte stores.
+// epilogue groups that split the accumulator columns) walk the output tiles round-robin.  The rings run continuously
+// across tiles and the accumulator is double-buffered in TMEM (2 x <= 256 columns): the epilogue of tile i overlaps
+// the MMAs of tile i+1.  The epilogue fuses bias + ReLU / sigmoid / tanh + the GRU gate arithmetic of
+// ptlflow/models/raft/update.py:58-73 and writes pixel-major f16/bf16 with 16-byte stores; its h / z / residual
+// operands are requested before the accumulator wait.  Launched with programmatic stream serialization: the
+// prologue (barriers, TMEM, tensor-map prefetch) overlaps the previous kernel's drain (pdl_wait below).
+// PFB_CONV_TRACE=<file> records a per-CTA timeline of every launch (tools/conv_trace_report.py).
+// What bounds it (findings 6-7): ~9 us of fixed cost per launch and a floor of ~135 clk per
+// tcgen05.mma (A-operand fetch), so only the N = 256 layers approach the nominal tensor rate.
 #include <stdio.h>
 #include <stdlib.h>
 
