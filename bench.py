@@ -110,17 +110,21 @@ class ClockSampler:
 
     def start(self):
         try:
+            # On a fresh box the first nvidia-smi of the boot takes seconds to attach to the driver and stalls the
+            # launching threads of a running CUDA process while it does: pay that once, synchronously, before anything
+            # is timed (measured: 23 ms/step instead of 9 when its start-up overlapped the timed loop).
+            subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
             self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
-        except OSError:
+        except (OSError, subprocess.TimeoutExpired):
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def wait_first_sample(self, timeout_s: float = 5.0):
+    def wait_first_sample(self, timeout_s: float = 60.0):
         """nvidia-smi's start-up (driver / NVML attach) stalls the launching threads of a running CUDA process for
         tens of milliseconds: let it finish before anything is timed."""
         t0 = time.perf_counter()
@@ -301,7 +305,7 @@ def run_ours(args):
             log("pipeline warm-up done")
 
         sampler.wait_first_sample()
-        time.sleep(0.2)
+        time.sleep(0.5)
         sampler.mark()
         if os.environ.get("PFB_BENCH_DEBUG"):  # diagnostics only: repeated untimed-for-the-record value loops
             for rep in range(3):

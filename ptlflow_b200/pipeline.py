@@ -16,6 +16,7 @@ This is host plumbing around ``model(inputs)``; it has no counterpart in the ref
 """
 from __future__ import annotations
 
+import os
 import queue
 import threading
 from concurrent.futures import Future
@@ -45,7 +46,7 @@ class _Result:
 
 
 class FramePipeline:
-    def __init__(self, model: torch.nn.Module, depth: int = 2, device: Optional[torch.device] = None):
+    def __init__(self, model: torch.nn.Module, depth: int = 2, device: Optional[torch.device] = None, prioritise_first: Optional[bool] = None):
         if depth < 1:
             raise ValueError("FramePipeline: depth must be >= 1")
         self.model = model
@@ -53,7 +54,12 @@ class FramePipeline:
         if self.device.type != "cuda":
             raise RuntimeError("FramePipeline needs a model on a CUDA device")
         self.depth = depth
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+        # prioritise_first: slot 0 on a high-priority stream.  When both slots have a kernel ready the scheduler then
+        # prefers slot 0, which pulls the slots out of lockstep (identical phases compete for the same resource; a
+        # tensor-bound phase next to an HBM-bound one do not).
+        if prioritise_first is None:
+            prioritise_first = bool(int(os.environ.get("PFB_PIPE_PRIORITY", "0")))
+        self.streams = [torch.cuda.Stream(device=self.device, priority=-1 if (prioritise_first and i == 0) else 0) for i in range(depth)]
         self._queues: List[queue.Queue] = [queue.Queue() for _ in range(depth)]
         self._dev_in: List[Optional[torch.Tensor]] = [None] * depth
         self._next = 0
