@@ -134,3 +134,59 @@ def test_gloo_world_size_2():
         assert p.exitcode == 0
     assert [(r[1], r[2]) for r in res] == [(0, 5), (5, 9)]
     assert all(r[3] == 11.0 and r[4] == 9.0 for r in res)
+
+
+def test_first_conv_pack_layout_matches_header():
+    """ops.pack_first_conv == the layout include/ptlflow_b200.h documents for pfb_first_conv7x7s2 (built element by element here)."""
+    from ptlflow_b200 import ops
+
+    w = torch.arange(64 * 3 * 7 * 7, dtype=torch.float32).reshape(64, 3, 7, 7) / 1000.0
+    pk = ops.pack_first_conv(w, torch.float32)  # [9][16 row groups][4 K groups][8 rows][8 elements]
+    assert pk.shape == (9, 16, 4, 8, 8) and pk.is_contiguous()
+    for j, p, co, t, c in [(0, 0, 5, 1, 0), (2, 1, 63, 7, 2), (8, 1, 0, 4, 1), (6, 0, 17, 3, 2), (3, 1, 9, 1, 0)]:
+        row, col = p * 64 + co, 4 * t + c
+        ky, kx = j - 2 * p, t - 1
+        assert pk[j, row // 8, col // 8, row % 8, col % 8].item() == pytest.approx(w[co, c, ky, kx].item())
+    # zero where the filter row / column falls outside 0..6, for the dummy window pixel t = 0 and the pad channel c = 3
+    dense = pk.permute(0, 1, 3, 2, 4).reshape(9, 128, 32)
+    assert not dense[0, 64:].any() and not dense[1, 64:].any()  # phase 1 sees input-row offsets 2..8 only
+    assert not dense[7, :64].any() and not dense[8, :64].any()  # phase 0 sees 0..6 only
+    assert not dense[:, :, 0:4].any() and not dense[:, :, 3::4].any()
+
+
+def test_flow_conv_pack_layout_matches_header():
+    from ptlflow_b200 import ops
+
+    w = torch.arange(128 * 2 * 7 * 7, dtype=torch.float32).reshape(128, 2, 7, 7) / 1000.0
+    pk = ops.pack_flow_conv(w, torch.float32)  # [7][16][8][8][8]
+    assert pk.shape == (7, 16, 8, 8, 8)
+    dense = pk.permute(0, 1, 3, 2, 4).reshape(7, 128, 64)
+    for ky, co, t, c in [(0, 0, 1, 0), (6, 127, 7, 3), (3, 64, 4, 2), (2, 9, 2, 1)]:
+        assert dense[ky, co, 8 * t + c].item() == pytest.approx(w[co, c & 1, ky, t - 1].item())  # hi and lo halves share the weight
+    assert not dense[:, :, 0:8].any()  # window pixel t = 0 lies left of the 7 taps
+    assert not dense.reshape(7, 128, 8, 8)[..., 4:].any()  # channels 4..7 of the 16-byte pixel are padding
+
+
+def test_pipeline_rejects_cpu_models_and_bad_depth():
+    import ptlflow_b200 as pb
+    from ptlflow_b200.pipeline import FramePipeline
+
+    m = pb.get_model("raft_small").eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FramePipeline(m, depth=2)
+    with pytest.raises(ValueError):
+        FramePipeline(m, depth=0)
+
+
+def test_cudnn_flags_first_in_last_out():
+    """Nested / concurrent forwards must not switch cuDNN's benchmark mode off under each other (models/raft/raft.py)."""
+    from ptlflow_b200.models.raft.raft import _cudnn_flags
+
+    cd = torch.backends.cudnn
+    before = (cd.enabled, cd.benchmark, cd.allow_tf32)
+    with _cudnn_flags(True, False):
+        assert cd.benchmark is True and cd.allow_tf32 is False
+        with _cudnn_flags(False, True):  # a second forward in flight: the first one's settings stay
+            assert cd.benchmark is True and cd.allow_tf32 is False
+        assert cd.benchmark is True  # ... also after the inner one has left
+    assert (cd.enabled, cd.benchmark, cd.allow_tf32) == before
