@@ -63,7 +63,6 @@ struct ConvUmmaArgs {
   int halo;
   int a_stages, a_slot_bytes, a_tx_bytes, b_stages, b_slot_bytes;
   int b_group, b_tap_bytes;      // weight stage = b_group consecutive taps of one activation patch (1, or all of them)
-  int desc_base_offset_mode;     // experiment knob: 1 = put (addr >> 7) & 7 into the descriptor base_offset field
   const float* bias;
   int epilogue;
   float scale;
@@ -600,7 +599,6 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   pick_tile(p->H, p->W, a.TW, a.TH);
   static const int env_halo = getenv("PFB_CONV_HALO") ? atoi(getenv("PFB_CONV_HALO")) : 1;
   static const int env_cg = getenv("PFB_CONV_CTA_PAIR") ? atoi(getenv("PFB_CONV_CTA_PAIR")) : 1;
-  static const int env_desc = getenv("PFB_UMMA_DESC_MODE") ? atoi(getenv("PFB_UMMA_DESC_MODE")) : 0;
   static const int env_vhalo = getenv("PFB_CONV_VHALO") ? atoi(getenv("PFB_CONV_VHALO")) : 1;
   a.halo = (env_halo && a.TH == 1 && p->KW > 1) ? 1 : 0;
   // (with all 256 output channels in one tile the 448-tile grid of the 8x16 patches costs a fourth round that the
@@ -618,7 +616,6 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
     }
     a.halo = 2;
   }
-  a.desc_base_offset_mode = env_desc;
   const int patch_w = a.TW + (a.halo == 1 ? p->KW - 1 : 0);
   const int patch_h = a.TH + (a.halo == 2 ? p->KH - 1 : 0);
   a.tw_shift = 0;

@@ -48,7 +48,7 @@ struct FcArgs {
   double* stats;      // [N][64][2] (sum, sum of squares of the fp32 accumulator + bias) or null
   int N, H, W, Ho, Wo;
   int pairs, nseg, n_items, per_cta;
-  int relu, ab_fmt, swap_lbo_sbo;
+  int relu, ab_fmt;
 };
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -168,11 +168,9 @@ __global__ void __launch_bounds__(576, 1) first_conv_umma_kernel(const FcArgs a)
     // ================= MMA issuer =================
     const uint32_t idesc = make_idesc_f16(128, 256, a.ab_fmt);
     // non-swizzled K-major descriptors: {addr >> 4, LBO >> 4 at bit 16} , {SBO >> 4, version 1 at bit 14}
-    uint32_t a_lbo = 128 >> 4, a_sbo = 512 >> 4, b_lbo = 16 >> 4, b_sbo = 128 >> 4;
-    if (a.swap_lbo_sbo) {
-      uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t;
-      t = b_lbo; b_lbo = b_sbo; b_sbo = t;
-    }
+    // LBO = byte distance between core matrices along K, SBO = along M / N (the reading that
+    // tests/test_gpu_ops.py::test_first_conv7x7s2_vs_torch confirms on B200)
+    const uint32_t a_lbo = 128 >> 4, a_sbo = 512 >> 4, b_lbo = 16 >> 4, b_sbo = 128 >> 4;
     const uint32_t a_hi = a_sbo | (1u << 14), b_hi = b_sbo | (1u << 14);
     const uint32_t a_lo0 = ((smem_u32(smemA) & 0x3FFFF) >> 4) | (a_lbo << 16);
     mbar_wait(&bars->a_full, 0);
@@ -485,8 +483,6 @@ extern "C" PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, con
   grid = ceil_div(a.n_items, a.per_cta);
   a.relu = relu;
   a.ab_fmt = dtype == PFB_F16 ? 0 : 1;
-  static const int env_swap = getenv("PFB_FC_DESC_SWAP") ? atoi(getenv("PFB_FC_DESC_SWAP")) : 0;
-  a.swap_lbo_sbo = env_swap;
   const size_t smem = kFcABytes + kFcSlots * kFcSlotBytes + 16 * 2048 + sizeof(FcBars) + 1024;
   ProfScope prof(KC_MISC, s);  // encoder side: not part of the update-block conv roofline
   if (dtype == PFB_F16) {
