@@ -53,6 +53,26 @@ def make_e2e() -> None:
         print(name, tuple(out["flows"].shape), "max|flow|", float(out["flows"].abs().max()))
 
 
+def make_warm_start() -> None:
+    """Warm start: the reference's forward_interpolate_batch (scipy) and a second forward started from it."""
+    ref_shim.load_raft()
+    import ptlflow.utils.utils as ref_utils
+
+    flow = torch.from_numpy(synth.synth_normal("ws/flow", (2, 2, 16, 24), 51, scale=4.0))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "op_forward_interpolate.npz"), recipe=_recipe(b=2, h=16, w=24, seed=51, scale=4.0),
+                        out=ref_utils.forward_interpolate_batch(flow).numpy().astype(np.float32))
+    model = ref_shim.build_reference_model("raft_small", seed=8, iters=3)
+    img = torch.from_numpy(synth.synth_images(1, 128, 160, seed=18, kind="smooth"))
+    with torch.no_grad():
+        first = model({"images": img})
+        second = model({"images": img, "prev_preds": {"flow_small": first["flow_small"]}})
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "e2e_raft_small_warm.npz"),
+                        recipe=_recipe(variant="raft_small", kwargs=dict(iters=3), batch=1, height=128, width=160, kind="smooth", wseed=8, iseed=18),
+                        first_flow_small=first["flow_small"].numpy().astype(np.float32),
+                        flows=second["flows"].numpy().astype(np.float32), flow_small=second["flow_small"].numpy().astype(np.float32))
+    print("warm start", tuple(second["flows"].shape), "max|flow|", float(second["flows"].abs().max()))
+
+
 def make_ops() -> None:
     """Operator-level vectors straight from the reference classes (CorrBlock, BasicUpdateBlock, ...)."""
     ref_corr = ref_shim.load_raft_corr()
@@ -136,6 +156,7 @@ def main() -> None:
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     make_ops()
     make_e2e()
+    make_warm_start()
     total = sum(os.path.getsize(os.path.join(GOLDEN_DIR, f)) for f in os.listdir(GOLDEN_DIR))
     print("golden bytes:", total)
 

@@ -423,3 +423,15 @@ def test_forward_interpolate_vs_scipy(b, h, w, scale):
     mismatch = ((got - ref).abs().amax(dim=1) > 0).float().mean().item()
     assert mismatch < 2e-3, f"{mismatch:.4f} of the pixels differ from scipy's nearest neighbour"
     assert torch.equal(forward_interpolate_batch(torch.full((1, 2, 6, 7), 1000.0, device=DEV)).cpu(), torch.zeros(1, 2, 6, 7))  # nothing lands inside
+
+
+def test_forward_interpolate_vs_reference_vector():
+    """pfb_forward_interpolate against the vector written by the reference's own forward_interpolate_batch."""
+    from helpers import load_golden
+    from ptlflow_b200.utils.warm_start import forward_interpolate_batch
+
+    recipe, g = load_golden("op_forward_interpolate")
+    flow = torch.from_numpy(synth.synth_normal("ws/flow", (recipe["b"], 2, recipe["h"], recipe["w"]), recipe["seed"], scale=recipe["scale"]))
+    got = forward_interpolate_batch(flow.to(DEV)).cpu().numpy()
+    mismatch = (np.abs(got - g["out"]).max(axis=1) > 0).mean()
+    assert mismatch < 2e-3, f"{mismatch:.4f} of the pixels differ from the reference (only exact distance ties may)"
