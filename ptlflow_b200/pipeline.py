@@ -136,3 +136,78 @@ class FramePipeline:
     def __exit__(self, *exc) -> None:
         self.drain()
         self.close()
+
+
+class FrameFeeder:
+    """Decodes frame pairs on worker threads and yields host batches ready for ``FramePipeline.submit``.
+
+    The reference's ``infer.py:178-231`` decodes with ``cv.imread`` on the critical path, one pair at a time; here the
+    decode of the next batches overlaps the GPU work of the current ones.  Yields ``(indices, images)`` with ``images``
+    a (pinned, when CUDA is present) ``[b,2,3,H,W]`` tensor in the reference's input convention (BGR, [0,1]); a batch
+    never mixes frame sizes."""
+
+    def __init__(self, pairs, batch: int = 8, dtype: torch.dtype = torch.float16, workers: int = 4, prefetch: int = 3, pin: Optional[bool] = None):
+        self.pairs = list(pairs)
+        self.batch, self.dtype, self.workers, self.prefetch = batch, dtype, workers, prefetch
+        self.pin = torch.cuda.is_available() if pin is None else pin
+
+    @staticmethod
+    def _decode(path) -> torch.Tensor:
+        import cv2
+
+        img = cv2.imread(str(path), cv2.IMREAD_COLOR)
+        if img is None:
+            raise FileNotFoundError(f"could not read image {path}")
+        return torch.from_numpy(img).permute(2, 0, 1)  # uint8 [3,H,W], BGR
+
+    def _make_batch(self, idx: List[int]):
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=self.workers) as ex:
+            frames = list(ex.map(self._decode, [p for i in idx for p in self.pairs[i]]))
+        groups: List[List[int]] = []
+        for k, i in enumerate(idx):  # split where the frame size changes
+            shp = tuple(frames[2 * k].shape)
+            if tuple(frames[2 * k + 1].shape) != shp:
+                raise ValueError(f"pair {i}: the two frames differ in size")
+            if groups and tuple(frames[2 * (groups[-1][0] - idx[0])].shape) == shp:
+                groups[-1].append(i)
+            else:
+                groups.append([i])
+        out = []
+        for g in groups:
+            k0 = g[0] - idx[0]
+            h, w = frames[2 * k0].shape[1:]
+            buf = torch.empty((len(g), 2, 3, h, w), dtype=self.dtype)
+            if self.pin:
+                buf = buf.pin_memory()
+            for j, i in enumerate(g):
+                k = i - idx[0]
+                buf[j, 0] = frames[2 * k].to(self.dtype) / 255.0
+                buf[j, 1] = frames[2 * k + 1].to(self.dtype) / 255.0
+            out.append((g, buf))
+        return out
+
+    def __iter__(self):
+        chunks = [list(range(i, min(i + self.batch, len(self.pairs)))) for i in range(0, len(self.pairs), self.batch)]
+        q: "queue.Queue" = queue.Queue(maxsize=max(1, self.prefetch))
+
+        def produce():
+            try:
+                for c in chunks:
+                    for item in self._make_batch(c):
+                        q.put(item)
+                q.put(None)
+            except BaseException as e:  # noqa: BLE001 -- re-raised in the consumer
+                q.put(e)
+
+        t = threading.Thread(target=produce, daemon=True, name="pfb-feeder")
+        t.start()
+        while True:
+            item = q.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+        t.join(timeout=60)
