@@ -28,13 +28,14 @@ import torch
 class _Result:
     """Outputs of one submitted batch; ``get()`` waits for the slot's stream to reach the end of that batch."""
 
-    def __init__(self, future: Future):
+    def __init__(self, future: Future, device: torch.device):
         self._future = future
+        self._device = device
 
     def get(self) -> Dict[str, torch.Tensor]:
         out, event = self._future.result()
         event.synchronize()
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self._device)
         for v in out.values():  # allocated on the slot's stream, consumed on the caller's
             if isinstance(v, torch.Tensor) and v.is_cuda:
                 v.record_stream(cur)
@@ -110,7 +111,7 @@ class FramePipeline:
         fut: Future = Future()
         extra = {k: v for k, v in inputs.items() if k != "images"}
         self._queues[slot].put((inputs["images"], extra, host_out, ready, fut))
-        res = _Result(fut)
+        res = _Result(fut, self.device)
         self._pending.append(res)
         return res
 
