@@ -53,6 +53,30 @@ def make_e2e() -> None:
         print(name, tuple(out["flows"].shape), "max|flow|", float(out["flows"].abs().max()))
 
 
+def make_gma_ops() -> None:
+    """GMA's Attention / Aggregate (gma_utils.py:32-113) as the reference's own modules compute them (heads = 1)."""
+    ref_shim.load_gma()
+    import ptlflow.models.gma.gma_utils as gu
+
+    b, c, h, w = 2, 128, 6, 9
+    att = gu.Attention(dim=c, heads=1, max_pos_size=160, dim_head=c, position_only=False, position_and_content=False).eval()
+    agg = gu.Aggregate(dim=c, dim_head=c, heads=1).eval()
+    sd = {"att.to_qk.weight": torch.from_numpy(synth.synth_tensor("att.to_qk.weight", tuple(att.to_qk.weight.shape), 71)),
+          "update_block.aggregator.to_v.weight": torch.from_numpy(synth.synth_tensor("update_block.aggregator.to_v.weight", tuple(agg.to_v.weight.shape), 71)),
+          "update_block.aggregator.gamma": torch.from_numpy(synth.synth_tensor("update_block.aggregator.gamma", (1,), 71))}
+    att.to_qk.weight.data.copy_(sd["att.to_qk.weight"])
+    agg.to_v.weight.data.copy_(sd["update_block.aggregator.to_v.weight"])
+    agg.gamma.data.copy_(sd["update_block.aggregator.gamma"])
+    inp = torch.relu(torch.from_numpy(synth.synth_normal("gma/inp", (b, c, h, w), 71)))
+    motion = torch.from_numpy(synth.synth_normal("gma/motion", (b, c, h, w), 71))
+    with torch.no_grad():
+        a = att(inp)  # [b, heads, N, N]
+        g = agg(a, motion)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "op_gma.npz"), recipe=_recipe(b=b, c=c, h=h, w=w, seed=71),
+                        attention=a.numpy().astype(np.float32), aggregate=g.numpy().astype(np.float32))
+    print("op_gma", tuple(a.shape), tuple(g.shape))
+
+
 def make_warm_start() -> None:
     """Warm start: the reference's forward_interpolate_batch (scipy) and a second forward started from it."""
     ref_shim.load_raft()
@@ -157,6 +181,7 @@ def main() -> None:
     make_ops()
     make_e2e()
     make_warm_start()
+    make_gma_ops()
     total = sum(os.path.getsize(os.path.join(GOLDEN_DIR, f)) for f in os.listdir(GOLDEN_DIR))
     print("golden bytes:", total)
 
