@@ -276,3 +276,55 @@ def test_frame_feeder_batches_and_splits_on_size(tmp_path):
     assert images.shape == (3, 2, 3, 24, 32)
     want = torch.from_numpy(paths[1][1][1]).permute(2, 0, 1).float() / 255.0  # pair 1, second frame, BGR as cv2 reads it
     assert torch.equal(images[1, 1], want)
+
+
+def test_overlapping_window_gemm_is_the_convolution():
+    """CPU emulation of csrc/first_conv.cu: the packed weight tiles times the overlapping 8-pixel windows of the raw
+    input rows (what the non-swizzled UMMA descriptor with LBO = 16 B, SBO = 128 B reads) equals the convolution.
+    Pins the operand contract written in include/ptlflow_b200.h without a GPU."""
+    import torch.nn.functional as F
+
+    from ptlflow_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+    # ---- first encoder convolution: 7x7, stride 2, 3 -> 64, 4-channel pixels, two output rows per accumulator
+    H, W = 12, 20
+    x = torch.randn(1, H, W, 4, generator=g)
+    x[..., 3] = 0
+    wt = torch.randn(64, 3, 7, 7, generator=g)
+    ref = F.conv2d(x[..., :3].permute(0, 3, 1, 2), wt, stride=2, padding=3)[0]  # [64, H/2, W/2]
+    tiles = ops.pack_first_conv(wt, torch.float32).permute(0, 1, 3, 2, 4).reshape(9, 128, 32)  # [j][p*64+co][4t+c]
+    Wo = W // 2
+    for y in range(0, H // 2, 2):
+        acc = torch.zeros(128, Wo)
+        for j in range(9):
+            r = 2 * y - 3 + j
+            if not 0 <= r < H:
+                continue  # rows outside the image contribute zero: the kernel skips their MMAs
+            row = torch.zeros((2 * Wo + 8) * 4)  # buffer pixel i <-> image pixel i - 4, zero halo
+            row[4 * 4 : 4 * 4 + W * 4] = x[0, r].reshape(-1)
+            windows = row.as_strided((Wo, 32), (8, 1))  # output pixel n reads 8 pixels x 4 channels starting 2 pixels further
+            acc += tiles[j] @ windows.T
+        assert torch.allclose(acc[:64], ref[:, y], atol=1e-4)
+        if y + 1 < H // 2:
+            assert torch.allclose(acc[64:], ref[:, y + 1], atol=1e-4)
+    # ---- convf1: 7x7, stride 1, 2 -> 128 on the hi/lo-split flow, 16-byte (8-channel) pixels
+    Hf, Wf = 6, 11
+    flow = torch.randn(1, Hf, Wf, 2, generator=g) * 5
+    wf = torch.randn(128, 2, 7, 7, generator=g)
+    reff = F.conv2d(flow.permute(0, 3, 1, 2), wf, padding=3)[0]
+    tf = ops.pack_flow_conv(wf, torch.float32).permute(0, 1, 3, 2, 4).reshape(7, 128, 64)
+    hi = flow.half().float()
+    lo = flow - hi
+    px = torch.zeros(1, Hf, Wf, 8)
+    px[..., 0:2], px[..., 2:4] = hi, lo
+    for y in range(Hf):
+        acc = torch.zeros(128, Wf)
+        for j in range(7):
+            r = y + j - 3
+            if not 0 <= r < Hf:
+                continue
+            row = torch.zeros((Wf + 8) * 8)
+            row[4 * 8 : 4 * 8 + Wf * 8] = px[0, r].reshape(-1)
+            acc += tf[j] @ row.as_strided((Wf, 64), (8, 1)).T
+        assert torch.allclose(acc, reff[:, y], atol=1e-3)
