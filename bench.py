@@ -74,7 +74,13 @@ def parse_args():
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 SIMT, 2 tcgen05")
-    ap.add_argument("--inflight", type=int, default=2, help="frame-pair batches in flight per GPU (ptlflow_b200.pipeline.FramePipeline); 1 = one stream")
+    ap.add_argument("--inflight", type=int, default=1, help="frame-pair batches in flight per GPU (ptlflow_b200.pipeline.FramePipeline); 1 = one stream")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="1: one CUDA graph launch per forward (default); 0: eager launches")
+    ap.add_argument("--fp32-context", action="store_true", help="accuracy mode: context encoder in fp32 (RAFT.enable_fp32_context)")
+    ap.add_argument("--protocol-samples", type=int, default=12, help="synchronised single forwards for the model_benchmark.py protocol (0 = skip)")
+    ap.add_argument("--sustained-seconds", type=float, default=5.0, help="length of the sustained loop (0 = skip)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -174,6 +180,10 @@ def algorithmic_work(model, B, H8, W8, iters, esize):
     per_iter, once = 0, 0
     for lid, pk in eng.layers.items():
         fl = 2 * pk.Cin * pk.KH * pk.KW * pk.Cout * P
+        if lid == _lib.L_FLOW2T and _lib.L_FLOW2 in eng.layers:
+            continue  # the tap form of flow_head.conv2 is the same layer as L_FLOW2: counted once
+        if lid == _lib.L_CONVF1 and eng.layers[lid].weight_k is not None:
+            continue  # convf1 on tcgen05 runs in its own kernel class (flowconv)
         if lid in (_lib.L_MASK1, _lib.L_MASK2):
             once += fl
         else:
@@ -185,15 +195,16 @@ def algorithmic_work(model, B, H8, W8, iters, esize):
     C = model.fnet.conv2.out_channels
     vol_elems = sum((H8 >> l) * (W8 >> l) for l in range(L))
     return {
-        "conv": {"flops": per_iter * iters + once, "launches_per_step": None},
+        "conv": {"flops": per_iter * iters + once},
         "lookup": {"bytes": lookup_bytes},
-        "volume": {"bytes": B * (2 * N * C * esize + N * (H8 * W8) * esize), "flops": 2 * B * N * N * C},
+        # a1 + a2 in one launch: both feature maps read once, every pyramid level written once
+        "volume": {"bytes": B * (2 * N * C * esize + N * vol_elems * esize), "flops": 2 * B * N * N * C},
         "pool": {"bytes": B * N * esize * (vol_elems - H8 * W8 + sum((H8 >> l) * (W8 >> l) for l in range(L - 1)))},
         "upsample": {"bytes": P * (576 * esize + 8) + B * 2 * 64 * N * 4},
     }
 
 
-KC_NAMES = ["volume", "pool", "lookup", "onthefly", "conv", "upsample", "misc"]
+KC_NAMES = ["volume", "pool", "lookup", "onthefly", "conv", "upsample", "misc", "enc_affine", "enc_stats", "enc_conv1", "flowconv", "gather"]
 
 
 def run_ours(args):
@@ -213,8 +224,12 @@ def run_ours(args):
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
     torch.manual_seed(1234)
     model = pb.get_model(args.model, args=Namespace(model=Namespace(iters=args.iters)))
+    sd_fp32 = {k: v.detach().clone() for k, v in model.state_dict().items()}  # the fp32 weights the reference would hold
+    if args.fp32_context:
+        model.enable_fp32_context()
     model = model.eval().to(dev).to(dtype)
     model.kernel_impl = args.kernel_impl
+    model.use_cuda_graph = bool(args.cuda_graph)
 
     B, H, W = args.batch, args.height, args.width
     pool = 3
@@ -223,13 +238,15 @@ def run_ours(args):
     devin = [h.to(dev) for h in host]
     host_out = torch.empty((B, 1, 2, H, W), dtype=dtype).pin_memory()
 
+    def launches_now():
+        return int(lib.pfb_launch_count(-1)) + int(model.graph_launches_replayed)
+
     def step_resident(i):
         return model({"images": devin[i % pool]})
 
-    # e2e pipeline: what a caller feeding frames from host memory runs.  Two device input slots; the H2D copy of
-    # step i+1 and the D2H copy of step i's flow ride a side stream while step i / i+1 computes (PCIe is full
-    # duplex).  Every step's input really comes from pinned host memory and every step's flow really lands in
-    # pinned host memory inside the timed region.
+    # e2e: what a caller feeding frames from host memory runs.  Two device input slots; the H2D copy of step i+1 and the
+    # D2H copy of step i's flow ride a side stream while step i / i+1 computes (PCIe is full duplex).  Every step's input
+    # really comes from pinned host memory and every step's flow really lands in pinned host memory inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
     dev_in = [torch.empty_like(devin[0]) for _ in range(2)]
     h2d_done = [torch.cuda.Event() for _ in range(2)]
@@ -263,9 +280,8 @@ def run_ours(args):
             flows.record_stream(copy_stream)
         main.wait_stream(copy_stream)
 
-    # Two batches in flight (ptlflow_b200.pipeline.FramePipeline: one stream + host thread per slot): the chain of
-    # ~250 dependent kernels of one forward leaves gaps that an independent second batch fills.  --inflight 1 keeps
-    # the single-stream loops above.
+    # --inflight > 1: several batches in flight (ptlflow_b200.pipeline.FramePipeline: one stream + host thread + CUDA graph
+    # per slot).  Default 1: one stream, one graph launch per forward -- the protocol of SURVEY.md section 8(d).
     pipe = None
     if args.inflight > 1:
         from ptlflow_b200.pipeline import FramePipeline
@@ -290,7 +306,7 @@ def run_ours(args):
                 pipe.submit({"images": host[i % pool]}, host_out=host_outs[i % args.inflight])
             pipe.drain()
 
-    log(f"model on {dev}, {args.dtype}, batch {B}, {args.inflight} batch(es) in flight; warming up")
+    log(f"model on {dev}, {args.dtype}, batch {B}, {args.inflight} batch(es) in flight, cuda graph {'on' if model.use_cuda_graph else 'off'}; warming up")
     sampler = ClockSampler(local_rank)
     sampler.start()
     with torch.no_grad():
@@ -298,105 +314,177 @@ def run_ours(args):
             step_resident(i)
             torch.cuda.synchronize()
             log(f"warm-up step {i} done")
-        if pipe is not None:  # the slots' threads tune cuDNN (thread-local cache) and allocate their scratch
+        if pipe is not None:  # the slots' threads tune cuDNN (thread-local cache), capture their graphs and allocate their scratch
             run_value(max(3, args.warmup) * args.inflight)
             run_e2e_any(args.inflight)
             torch.cuda.synchronize()
             log("pipeline warm-up done")
+        run_e2e_any(2)
+        torch.cuda.synchronize()
 
         sampler.wait_first_sample()
         time.sleep(0.5)
-        if pipe is not None:
-            # Pre-roll: an untimed copy of the timed loop immediately before it.  The first K-deep pipelined loop of
-            # the first CUDA process on a fresh box has been seen to run 2-3x slow once (17-33 ms/step, the loops after
-            # it at 9); warm-up steps in the strict sense, on the exact code path that is timed next.
-            run_value(args.steps)
-            torch.cuda.synchronize()
+        run_value(args.steps)  # pre-roll: an untimed copy of the timed loop right before it
+        torch.cuda.synchronize()
         sampler.mark()
 
-        def timed_value():
+        def timed(fn, n):
             sharding.barrier(); torch.cuda.synchronize()
-            n0 = lib.pfb_launch_count(-1)
+            n0 = launches_now()
+            t0 = time.perf_counter()
             v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             v0.record()
-            run_value(args.steps)
+            fn(n)
             v1.record()
-            torch.cuda.synchronize(); sharding.barrier()
-            return sharding.max_over_ranks(v0.elapsed_time(v1), dev), lib.pfb_launch_count(-1) - n0
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            sharding.barrier()
+            return sharding.max_over_ranks(max(v0.elapsed_time(v1), 0.0), dev), sharding.max_over_ranks(wall_ms, dev), launches_now() - n0
 
-        # ---- value: device-resident inputs ----
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ms_value, launches = timed_value()
-        log(f"resident: {ms_value / args.steps:.2f} ms/step")
-
+        # ---- value: device-resident inputs, exactly K steps ----
+        ms_value, _, launches = timed(run_value, args.steps)
+        log(f"resident: {ms_value / args.steps:.3f} ms/step")
         # ---- e2e: pinned host inputs, H2D + forward + D2H of the flow every step ----
-        run_e2e_any(2)
-        sharding.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e0.record()
-        run_e2e_any(args.steps)
-        e1.record()
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        sharding.barrier()
-        ms_e2e = sharding.max_over_ranks(max(e0.elapsed_time(e1), wall_ms), dev)
-        # the resident loop does strictly less work per step than the end-to-end loop: if it came out clearly slower,
-        # it caught a transient -- re-measured once (same K steps), and said so in the JSON line
+        ms_e2e_ev, ms_e2e_wall, _ = timed(run_e2e_any, args.steps)
+        ms_e2e = max(ms_e2e_ev, ms_e2e_wall)
         value_remeasured = False
-        if ms_value > 1.25 * ms_e2e:
-            ms_value, launches = timed_value()
+        if ms_value > 1.25 * ms_e2e:  # the resident loop does strictly less work: a slower reading caught a transient
+            ms_value, _, launches = timed(run_value, args.steps)
             value_remeasured = True
-            log(f"resident (re-measured): {ms_value / args.steps:.2f} ms/step")
+            log(f"resident (re-measured): {ms_value / args.steps:.3f} ms/step")
         clocks = sampler.stop()
-        log(f"e2e: {ms_e2e / args.steps:.2f} ms/step; clocks {clocks}")
+        log(f"e2e: {ms_e2e / args.steps:.3f} ms/step; clocks {clocks}")
 
-        # ---- instrumented pass: live per-kernel-class durations (not part of the numbers above) ----
+        # ---- protocol of the reference's model_benchmark.py:421-466: fresh torch.rand per sample
+        # (made on the CPU, moved and converted OUTSIDE the timed region), synchronise before and after every single
+        # forward, first forward dropped, median ----
+        proto = None
+        if args.protocol_samples > 0:
+            times = []
+            gp = torch.Generator().manual_seed(555 + rank)
+            for i in range(args.protocol_samples + 1):
+                x = torch.rand(B, 2, 3, H, W, generator=gp).to(dev).to(dtype)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                model({"images": x})
+                torch.cuda.synchronize()
+                if i > 0:
+                    times.append((time.perf_counter() - t0) * 1e3)
+            med = statistics.median(times)
+            med = sharding.max_over_ranks(med, dev)
+            proto = {"what": "median wall time of synchronised single forwards on fresh torch.rand frames (model_benchmark.py:421-466), one stream",
+                     "samples": len(times), "median_ms": round(med, 4), "min_ms": round(min(times), 4), "max_ms": round(max(times), 4),
+                     "value": round(B * world / (med * 1e-3), 2), "unit": "pairs/s"}
+            log(f"protocol: median {med:.3f} ms per synchronised forward")
+
+        # ---- sustained: the resident loop for >= N seconds (the K-step number above is a burst of ~0.1 s) ----
+        sustained = None
+        if args.sustained_seconds > 0:
+            per = max(1e-3, ms_value / args.steps)
+            n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / per) + 1)
+            s2 = ClockSampler(local_rank)
+            s2.start(); s2.wait_first_sample(); s2.mark()
+            ms_sus, _, _ = timed(run_value, n_sus)
+            c2 = s2.stop()
+            sustained = {"seconds": round(ms_sus * 1e-3, 2), "steps": n_sus, "ms_per_step": round(ms_sus / n_sus, 4),
+                         "value": round(B * n_sus * world / (ms_sus * 1e-3), 2), "unit": "pairs/s", "clocks": c2}
+            log(f"sustained: {ms_sus / n_sus:.3f} ms/step over {ms_sus * 1e-3:.1f} s")
+
+        # ---- strong scaling beside weak: the SAME 8 pairs split over the ranks ----
+        strong = None
+        if world > 1 and B % world == 0:
+            bs = B // world
+            sub = [d[:bs].contiguous() for d in devin]
+            for i in range(3):
+                model({"images": sub[i % pool]})
+            ms_st, _, _ = timed(lambda n: [model({"images": sub[i % pool]}) for i in range(n)], args.steps)
+            strong = {"total_pairs_per_step": B, "pairs_per_step_per_gpu": bs, "ms_per_step": round(ms_st / args.steps, 4),
+                      "value": round(B * args.steps / (ms_st * 1e-3), 2), "unit": "pairs/s"}
+
+        # ---- output check (outside every timed region): this run's flow against the fp32 oracle on the same frames ----
+        parity = None
+        if rank == 0 and not args.no_parity:
+            parity = parity_check(args, model, sd_fp32, devin[0], dev)
+            log(f"parity: {parity}")
+
+        # ---- instrumented pass: live per-kernel-class durations, eager launches (not part of the numbers above) ----
         prof_steps = 2
+        was_graph = model.use_cuda_graph
+        model.use_cuda_graph = False
+        step_resident(0)
+        torch.cuda.synchronize()
         lib.pfb_profile_enable(1)
+        t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_ev0.record()
         for i in range(prof_steps):
             step_resident(i)
-        ms_arr, n_arr = (C.c_double * 8)(), (C.c_ulonglong * 8)()
-        _lib.check(lib.pfb_profile_collect(ms_arr, n_arr, 8), "profile_collect")
+        t_ev1.record()
+        ms_arr, n_arr = (C.c_double * 16)(), (C.c_ulonglong * 16)()
+        _lib.check(lib.pfb_profile_collect(ms_arr, n_arr, 16), "profile_collect")
         lib.pfb_profile_enable(0)
+        ms_prof_step = t_ev0.elapsed_time(t_ev1) / prof_steps
+        model.use_cuda_graph = was_graph
         log("instrumented pass done")
         if pipe is not None:
             pipe.close()
+
+        comparators = None
+        if rank == 0 and world == 1 and not args.no_comparators:
+            comparators = same_gpu_comparators(args, dev)
+            log(f"same-GPU comparators: {comparators}")
 
     H8, W8 = (H + 7) // 8, (W + 7) // 8
     esize = 4 if dtype == torch.float32 else 2
     work = algorithmic_work(model, B, H8, W8, args.iters, esize)
     peaks = load_peaks()
     kernels = {}
+    ours_ms = 0.0
     for kc, name in enumerate(KC_NAMES):
         if n_arr[kc] == 0:
             continue
         ms_step = ms_arr[kc] / prof_steps
+        ours_ms += ms_step
         ent = {"ms_per_step": round(ms_step, 4), "launches_per_step": int(n_arr[kc] // prof_steps)}
         w = work.get(name, {})
         if "flops" in w and name == "conv":
             ent["tflops"] = round(w["flops"] / (ms_step * 1e-3) / 1e12, 2)
+            ent["frac_of_bf16_burst_peak"] = round(ent["tflops"] / peaks["bf16_tflops"], 4)
             ent["frac_of_bf16_sustained_peak"] = round(ent["tflops"] / peaks["bf16_tflops_sustained"], 4)
         if "bytes" in w:
             ent["algorithmic_gbs"] = round(w["bytes"] / (ms_step * 1e-3) / 1e9, 1)
             ent["frac_of_hbm_peak"] = round(ent["algorithmic_gbs"] / peaks["hbm_gbs"], 4)
         kernels[name] = ent
-    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    kernels["_not_this_library"] = {"ms_per_step": round(max(0.0, ms_prof_step - ours_ms), 4),
+                                    "what": "cuDNN encoder convolutions + torch glue: instrumented step time minus this library's classes"}
+    cand = {k: v for k, v in kernels.items() if not k.startswith("_")}
+    dominant = max(cand, key=lambda k: cand[k]["ms_per_step"]) if cand else None
     roofline = None
     if dominant == "conv":
         e = kernels["conv"]
         traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of the same command
-        tpath = os.path.join(ROOT, "profiles", "r01_conv_umma_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = round(json.load(f)["dram_bytes_per_launch"])
+        for tname in ("r02_conv_umma_traffic.json", "r01_conv_umma_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    traffic = round(json.load(f)["dram_bytes_per_launch"])
+                break
+        # the timed region is a burst (~0.1 s at ~1.9 GHz), so the burst bf16 peak is the matching denominator
         roofline = {"kernel": "update-block conv (implicit GEMM, tcgen05)", "bound": "tensor", "achieved": e["tflops"],
-                    "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": e["frac_of_bf16_sustained_peak"],
-                    "traffic": traffic, "peak_source": peaks["_source"] + ", sustained bf16 GEMM",
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": e["frac_of_bf16_burst_peak"],
+                    "frac_of_sustained_peak": e["frac_of_bf16_sustained_peak"],
+                    "traffic": traffic, "peak_source": peaks["_source"] + ", burst bf16 GEMM",
                     "algorithmic_flops_per_launch": round(work["conv"]["flops"] / max(1, e["launches_per_step"]))}
     elif dominant is not None and "algorithmic_gbs" in kernels[dominant]:
         e = kernels[dominant]
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": e["algorithmic_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": e["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["_source"]}
+    # north_star's headline fraction: correlation volume build + all lookups against the HBM roofline
+    corr_frac = None
+    if "volume" in kernels and "lookup" in kernels:
+        t_corr = (kernels["volume"]["ms_per_step"] + kernels["lookup"]["ms_per_step"]) * 1e-3
+        bytes_corr = work["volume"]["bytes"] + work["lookup"]["bytes"]
+        corr_frac = {"algorithmic_bytes_per_step": int(bytes_corr), "ms_per_step": round(t_corr * 1e3, 4),
+                     "achieved_gbs": round(bytes_corr / t_corr / 1e9, 1), "frac_of_hbm_peak": round(bytes_corr / t_corr / 1e9 / peaks["hbm_gbs"], 4)}
 
     pairs = B * args.steps * world
     value = pairs / (ms_value * 1e-3)
@@ -408,7 +496,9 @@ def run_ours(args):
         "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " storage, f32 accumulate/coordinates",
         "data": "synthetic (torch.rand frames, random-init weights, seed 1234)",
         "config": {"workload": f"{args.model} {W}x{H} {args.iters} iters, batch {B} per GPU (BASELINE.json configs[1])",
-                   "pairs_per_step_per_gpu": B, "batches_in_flight_per_gpu": args.inflight, "value_remeasured": value_remeasured, "parallelism": f"replicas x{world}, frame pairs sharded, no data-path collective",
+                   "pairs_per_step_per_gpu": B, "batches_in_flight_per_gpu": args.inflight, "cuda_graph": bool(model.use_cuda_graph),
+                   "fp32_context": bool(args.fp32_context), "value_remeasured": value_remeasured,
+                   "parallelism": f"replicas x{world}, frame pairs sharded, no data-path collective",
                    "l2": "per-step working set (>= 1 GB correlation pyramid at batch 8) exceeds the 126 MB L2; inputs rotate over a pool of 3 batches",
                    "kernel_impl": args.kernel_impl},
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "ms_per_step": round(ms_e2e / args.steps, 4),
@@ -417,7 +507,13 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "corr_hbm_roofline": corr_frac,
+        "protocol": proto,
+        "sustained": sustained,
+        "strong_scaling": strong,
+        "parity": parity,
         "kernels": kernels,
+        "same_gpu_comparators": comparators,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(args, args.cpu_baseline_seconds)
@@ -425,6 +521,87 @@ def run_ours(args):
         print(json.dumps(result), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def parity_check(args, model, sd_fp32, frames, dev):
+    """One forward of the benchmarked model object on (a 2-pair subset of) the benchmarked frames against the fp32 oracle
+    run on the same GPU with the model's ORIGINAL fp32 weights (before ``.half()``).  Outside every timed region."""
+    from oracle import raft_oracle as O
+
+    n = min(2, frames.shape[0])
+    x = frames[:n].contiguous()
+    sd = {k: v.to(dev) for k, v in sd_fp32.items()}
+    with torch.no_grad(), O.fp32_strict():
+        ref = O.raft_forward(sd, x.float(), args.model, iters=args.iters)["flows"]
+        out = model({"images": x})["flows_fp32"].float()
+    d = (out - ref).abs()
+    return {"max_abs_px": round(d.max().item(), 5), "mean_abs_px": round(d.mean().item(), 6), "max_flow_px": round(ref.abs().max().item(), 3),
+            "pairs": n, "against": "oracle/raft_oracle.py in fp32 (TF32 off) on the same GPU, holding the model's fp32 weights from before .half()"}
+
+
+def same_gpu_comparators(args, dev):
+    """The reference's algorithm as plain PyTorch-CUDA ops (the oracle port) on the same B200, same workload, timed with the
+    model_benchmark.py protocol: fp32 with TF32 off, and half precision like ``model.half()``.  Reported baselines."""
+    from oracle import raft_oracle as O
+    from oracle import synth
+
+    out = {}
+    sd32 = {k: v.to(dev) for k, v in synth.synth_state_dict(O.state_dict_shapes(args.model), 1234).items()}
+    B = args.batch
+    for name, half in (("pytorch_cuda_fp32_tf32_off", False), ("pytorch_cuda_half", True)):
+        try:
+            sd = {k: (v.half() if (half and v.is_floating_point()) else v) for k, v in sd32.items()}
+            fwd = _half_forward if half else O.raft_forward
+            times = []
+            for i in range(4):
+                x = torch.rand(B, 2, 3, args.height, args.width).to(dev)
+                x = x.half() if half else x
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    if half:
+                        fwd(sd, x, args.model, args.iters)
+                    else:
+                        with O.fp32_strict():
+                            fwd(sd, x, args.model, iters=args.iters)
+                torch.cuda.synchronize()
+                if i > 0:
+                    times.append((time.perf_counter() - t0) * 1e3)
+            med = statistics.median(times)
+            out[name] = {"median_ms": round(med, 3), "value": round(B / (med * 1e-3), 2), "unit": "pairs/s", "samples": len(times),
+                         "kind": "port (oracle/raft_oracle.py ops on CUDA tensors)", "batch": B}
+        except Exception as e:  # noqa: BLE001 -- a comparator must never take the bench line down
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def _half_forward(sd, images, variant, iters):
+    """raft_forward with every tensor in half precision (what ``model.half()`` does to the reference): the oracle casts to
+    fp32 internally, so this wrapper re-implements the cast policy by monkey-free means: run the same functions on half tensors."""
+    from oracle import raft_oracle as O
+
+    small, hdim, cdim, _f, cnorm, radius = O.VARIANTS[variant]
+    x, pads = O.preprocess(images)
+    img1, img2 = x[:, 0], x[:, 1]
+    b = img1.shape[0]
+    fmaps = O.encoder(torch.cat([img1, img2], 0), sd, "fnet.", "instance", small)
+    fmap1, fmap2 = fmaps[:b], fmaps[b:]
+    cnet = O.encoder(img1, sd, "cnet.", cnorm, small)
+    net, inp = torch.tanh(cnet[:, :hdim]), torch.relu(cnet[:, hdim:hdim + cdim])
+    pyr = O.corr_pyramid(O.corr_volume(fmap1, fmap2), 4)
+    h8, w8 = fmap1.shape[-2:]
+    coords0 = O.coords_grid(b, h8, w8, dtype=images.dtype, device=images.device)
+    coords1 = coords0.clone()
+    block = O.small_update_block if small else O.basic_update_block
+    mask = None
+    for _ in range(iters):
+        corr = O.corr_lookup(pyr, coords1, radius)
+        net, mask, delta = block(net, inp, corr, coords1 - coords0, sd)
+        coords1 = coords1 + delta
+    flow_small = coords1 - coords0
+    up = O.upflow8(flow_small) if mask is None else O.convex_upsample(flow_small, mask)
+    return O.unpad(up, pads)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -67,6 +67,13 @@ PFB_API int pfb_device_arch(void);
  * ---------------------------------------------------------------------------------- */
 PFB_API int pfb_corr_volume_build(const void* fmap1, const void* fmap2, void* const* pyramid, int B, int H, int W,
                           int C, int levels, pfb_dtype dtype, int impl, pfb_stream stream);
+/* Generalisation for the sibling corr.py copies: the queries are the H1 x W1 grid of fmap1, the targets
+ * the H2 x W2 grid of fmap2 (SEA-RAFT builds one volume per level against a separately resized fmap2,
+ * ptlflow/models/sea_raft/corr.py:77-83), and the scale is explicit (FlowFormer's cost volume is unscaled,
+ * ptlflow/models/flowformer/encoder.py:543-561).  pyramid[l] : [B*H1*W1, H2>>l, W2>>l].
+ * pfb_corr_volume_build(..., H, W, C, ...) == pfb_corr_volume_build_ex(..., H, W, H, W, C, levels, 1/sqrt(C), ...). */
+PFB_API int pfb_corr_volume_build_ex(const void* fmap1, const void* fmap2, void* const* pyramid, int B, int H1, int W1, int H2, int W2,
+                                     int C, int levels, float scale, pfb_dtype dtype, int impl, pfb_stream stream);
 /* bytes of level l for the given feature-grid size (helper for callers that allocate). */
 PFB_API size_t pfb_corr_level_bytes(int B, int H, int W, int level, pfb_dtype dtype);
 
@@ -81,6 +88,12 @@ PFB_API size_t pfb_corr_level_bytes(int B, int H, int W, int level, pfb_dtype dt
 PFB_API int pfb_corr_lookup(void* const* pyramid, const float* coords, void* out, int B, int H, int W, int levels,
                     int radius, pfb_dtype dtype, pfb_dtype out_dtype, int out_nchw, int out_stride,
                     pfb_stream stream);
+
+/* Same with explicit level sizes (level_h[l] x level_w[l] instead of H>>l x W>>l): pyramids whose levels were built one by one
+ * (pfb_corr_volume_build_ex) or whose target grid differs from the query grid.  level l is still sampled at coords / 2^l. */
+PFB_API int pfb_corr_lookup_ex(void* const* pyramid, const int* level_h, const int* level_w, const float* coords, void* out, int B,
+                               int H, int W, int levels, int radius, pfb_dtype dtype, pfb_dtype out_dtype, int out_nchw,
+                               int out_stride, pfb_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * a4: on-the-fly correlation + lookup (no 4D volume)
@@ -327,11 +340,13 @@ PFB_API int pfb_bias_act(const void* x, const float* bias, const void* residual,
 
 /* ------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): launch accounting and live per-kernel-class timing.
- * kernel_class: 0 volume, 1 pool, 2 lookup, 3 on-the-fly lookup, 4 conv, 5 upsample, 6 misc;
+ * kernel_class: 0 volume, 1 pool, 2 lookup, 3 on-the-fly lookup, 4 update-block conv (tcgen05 / SIMT), 5 upsample,
+ * 6 misc (packing, coords, softmax, transposes), 7 encoder normalise / bias / activation passes, 8 encoder instance-norm
+ * statistics, 9 first encoder convolution (tcgen05), 10 convf1 (7x7 on the flow, tcgen05), 11 flow-head tap gather;
  * -1 = all.  pfb_profile_collect synchronises the device, writes summed milliseconds and span
  * counts per class (arrays of >= PFB_KERNEL_CLASSES entries) and clears the recorded spans.
  * ---------------------------------------------------------------------------------- */
-#define PFB_KERNEL_CLASSES 7
+#define PFB_KERNEL_CLASSES 12
 PFB_API unsigned long long pfb_launch_count(int kernel_class);
 PFB_API int pfb_profile_enable(int on);
 PFB_API int pfb_profile_collect(double* ms, unsigned long long* n, int len);

@@ -12,6 +12,10 @@ pins it against vectors produced by the real reference (oracle/make_golden.py).
 
 Parity status: PINNED against tests/golden/*.npz (reference outputs generated in the
 build container).  Tolerance used by the pin: 2e-4 max-abs on flows for <= 12 iterations.
+
+The functions follow the device of their inputs, so the same restatement also runs on CUDA tensors
+(fp32, TF32 off: ``fp32_strict()`` below): that is how the parity tests check the BASELINE-sized shapes
+in seconds and how bench.py times a same-GPU PyTorch comparator.  It stays the checker in both roles.
 """
 from __future__ import annotations
 
@@ -23,6 +27,19 @@ import torch.nn.functional as F
 
 Tensor = torch.Tensor
 SD = Dict[str, Tensor]
+
+
+class fp32_strict:
+    """Context manager: true fp32 on CUDA (no TF32 in matmul / cuDNN), restored on exit."""
+
+    def __enter__(self):
+        self._saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self._saved
 
 
 # --------------------------------------------------------------------------------------
@@ -153,7 +170,7 @@ def corr_lookup(pyramid: Sequence[Tensor], coords: Tensor, radius: int) -> Tenso
     n = b * h * w
     cx = coords[:, 0].reshape(n, 1, 1)
     cy = coords[:, 1].reshape(n, 1, 1)
-    d = torch.arange(-radius, radius + 1, dtype=coords.dtype)
+    d = torch.arange(-radius, radius + 1, dtype=coords.dtype, device=coords.device)
     k = 2 * radius + 1
     outs = []
     for lvl, vol in enumerate(pyramid):
@@ -193,9 +210,9 @@ def alt_cuda_corr_forward(fmap1: Tensor, fmap2: Tensor, coords: Tensor, radius: 
     return corr_lookup([v], cc, radius).unsqueeze(1)
 
 
-def coords_grid(b: int, h: int, w: int, dtype=torch.float32) -> Tensor:
+def coords_grid(b: int, h: int, w: int, dtype=torch.float32, device=None) -> Tensor:
     """[B,2,H,W], channel 0 = x, channel 1 = y.  ptlflow/models/raft/utils.py:84-91."""
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=dtype), torch.arange(w, dtype=dtype), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=dtype, device=device), torch.arange(w, dtype=dtype, device=device), indexing="ij")
     return torch.stack([xs, ys], dim=0)[None].repeat(b, 1, 1, 1)
 
 
@@ -274,7 +291,7 @@ def convex_upsample(flow: Tensor, mask: Tensor) -> Tensor:
     b, _, h, w = flow.shape
     m = torch.softmax(mask.view(b, 9, 8, 8, h, w), dim=1)
     f = F.pad(8.0 * flow, (1, 1, 1, 1))
-    out = torch.zeros(b, 2, 8, 8, h, w, dtype=flow.dtype)
+    out = torch.zeros(b, 2, 8, 8, h, w, dtype=flow.dtype, device=flow.device)
     for tap in range(9):
         dy, dx = tap // 3, tap % 3
         nb = f[:, :, dy : dy + h, dx : dx + w]  # [B,2,H,W]
@@ -356,7 +373,7 @@ def raft_forward(
 
     pyramid = None if alternate_corr else corr_pyramid(corr_volume(fmap1, fmap2), corr_levels)
     h8, w8 = fmap1.shape[-2:]
-    coords0 = coords_grid(b, h8, w8)
+    coords0 = coords_grid(b, h8, w8, device=fmap1.device)
     coords1 = coords0.clone() if flow_init is None else coords0 + flow_init
     if trace is not None:
         trace.update(fmap1=fmap1, fmap2=fmap2, net0=net, inp=inp, lookups=[], nets=[], deltas=[])

@@ -103,7 +103,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-enum KernelClass { KC_VOLUME = 0, KC_POOL, KC_LOOKUP, KC_ONTHEFLY, KC_CONV, KC_UPSAMPLE, KC_MISC, KC_COUNT };
+enum KernelClass { KC_VOLUME = 0, KC_POOL, KC_LOOKUP, KC_ONTHEFLY, KC_CONV, KC_UPSAMPLE, KC_MISC,
+                   KC_ENC_AFFINE, KC_ENC_STATS, KC_ENC_CONV1, KC_FLOWCONV, KC_GATHER, KC_COUNT };
 class ProfScope {
  public:
   ProfScope(int kc, cudaStream_t s);
@@ -126,7 +127,7 @@ int conv_cout2_flow(const pfb_conv_params* p, cudaStream_t s);
 bool conv_flow7x7_supported(const pfb_conv_params* p);
 int conv_flow7x7(const pfb_conv_params* p, cudaStream_t s);
 // corr_umma.cu
-int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, int H, int W, int C, int L,
+int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, int N1, int H, int W, int C, int L, float scale,
                      pfb_dtype dt, cudaStream_t s);
 bool corr_volume_umma_supported(int B, int H, int W, int C, int L, pfb_dtype dt);
 

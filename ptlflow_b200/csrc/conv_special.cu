@@ -283,7 +283,7 @@ extern "C" PFB_API int pfb_flow_tap_gather(const float* taps, int tstride, const
                                            int W, pfb_stream stream) {
   PFB_CHECK_ARG(taps && coords && flow && B > 0 && H > 0 && W > 0 && tstride >= 18 && tstride % 2 == 0, "flow_tap_gather: bad arguments");
   cudaStream_t s = as_stream(stream);
-  ProfScope prof(KC_CONV, s);
+  ProfScope prof(KC_GATHER, s);
   launch_pdl(flow_tap_gather_kernel, dim3(ceil_div(B * H * W, 256)), dim3(256), 0, s, taps, tstride, bias, coords, flow, B, H, W);
   PFB_LAUNCH_CHECK();
   return PFB_OK;

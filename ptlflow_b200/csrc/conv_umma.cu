@@ -27,6 +27,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "umma.cuh"
 
 namespace pfb {
@@ -563,8 +565,14 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
 template <typename T, int CG>
 static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const ConvUmmaArgs& a, int grid, size_t smem,
                             cudaStream_t s) {
-  // per launch (cheap, and correct when one process drives several devices)
-  PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  // once per (instantiation, device): correct when one process drives several devices, and off the per-launch path
+  static std::atomic<unsigned long long> attr_done{0};
+  int dev = 0;
+  PFB_CUDA(cudaGetDevice(&dev));
+  if (!(attr_done.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
+    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(320);

@@ -13,7 +13,7 @@ namespace pfb {
 // =====================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) corr_volume_simt_kernel(const T* __restrict__ f1, const T* __restrict__ f2,
-                                                               T* __restrict__ out, int N, int C, float scale) {
+                                                               T* __restrict__ out, int N1, int N2, int C, float scale) {
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
@@ -22,16 +22,16 @@ __global__ void __launch_bounds__(256) corr_volume_simt_kernel(const T* __restri
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int lrow = tid >> 2, lk = (tid & 3) * 4;  // loader: row 0..63, 4 consecutive channels
-  const T* a_base = f1 + (size_t)b * N * C;
-  const T* b_base = f2 + (size_t)b * N * C;
+  const T* a_base = f1 + (size_t)b * N1 * C;
+  const T* b_base = f2 + (size_t)b * N2 * C;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < C; k0 += BK) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = k0 + lk + j;
       int ra = m0 + lrow, rb = n0 + lrow;
-      As[lk + j][lrow] = (ra < N && k < C) ? to_f32(a_base[(size_t)ra * C + k]) : 0.f;
-      Bs[lk + j][lrow] = (rb < N && k < C) ? to_f32(b_base[(size_t)rb * C + k]) : 0.f;
+      As[lk + j][lrow] = (ra < N1 && k < C) ? to_f32(a_base[(size_t)ra * C + k]) : 0.f;
+      Bs[lk + j][lrow] = (rb < N2 && k < C) ? to_f32(b_base[(size_t)rb * C + k]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -48,15 +48,15 @@ __global__ void __launch_bounds__(256) corr_volume_simt_kernel(const T* __restri
     }
     __syncthreads();
   }
-  T* o = out + (size_t)b * N * N;
+  T* o = out + (size_t)b * N1 * N2;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int m = m0 + ty * 4 + i;
-    if (m >= N) continue;
+    if (m >= N1) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
-      if (n < N) o[(size_t)m * N + n] = from_f32<T>(acc[i][j] * scale);
+      if (n < N2) o[(size_t)m * N2 + n] = from_f32<T>(acc[i][j] * scale);
     }
   }
 }
@@ -326,12 +326,13 @@ __global__ void __launch_bounds__(128) corr_onthefly_kernel(const T* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-static int fill_levels(LevelTable& lv, void* const* ptrs, int H, int W, int levels) {
+static int fill_levels(LevelTable& lv, void* const* ptrs, int H, int W, int levels, const int* level_h = nullptr,
+                       const int* level_w = nullptr) {
   for (int l = 0; l < levels; ++l) {
     if (!ptrs[l]) return -1;
     lv.ptr[l] = ptrs[l];
-    lv.h[l] = H >> l;
-    lv.w[l] = W >> l;
+    lv.h[l] = level_h ? level_h[l] : H >> l;
+    lv.w[l] = level_w ? level_w[l] : W >> l;
     if (lv.h[l] < 1 || lv.w[l] < 1) return -2;
   }
   return 0;
@@ -352,19 +353,18 @@ static int launch_pool(const void* in, void* out, size_t N, int H, int W, int C,
   return PFB_OK;
 }
 
-int corr_volume_simt(const void* f1, const void* f2, void* const* pyr, int B, int H, int W, int C, int L,
+int corr_volume_simt(const void* f1, const void* f2, void* const* pyr, int B, int N1, int H, int W, int C, int L, float scale,
                      pfb_dtype dt, cudaStream_t s) {
-  const int N = H * W;
-  const float scale = 1.0f / sqrtf((float)C);
-  dim3 grid(ceil_div(N, 64), ceil_div(N, 64), B);
+  const int N2 = H * W;
+  dim3 grid(ceil_div(N2, 64), ceil_div(N1, 64), B);
   PFB_DISPATCH_DTYPE(dt, T, {
     { ProfScope prof(KC_VOLUME, s);
     corr_volume_simt_kernel<T><<<grid, 256, 0, s>>>(reinterpret_cast<const T*>(f1),
                                                     reinterpret_cast<const T*>(f2),
-                                                    reinterpret_cast<T*>(pyr[0]), N, C, scale); }
+                                                    reinterpret_cast<T*>(pyr[0]), N1, N2, C, scale); }
     PFB_LAUNCH_CHECK();
     for (int l = 1; l < L; ++l) {
-      int rc = launch_pool<T>(pyr[l - 1], pyr[l], (size_t)B * N, H >> (l - 1), W >> (l - 1), 1, s);
+      int rc = launch_pool<T>(pyr[l - 1], pyr[l], (size_t)B * N1, H >> (l - 1), W >> (l - 1), 1, s);
       if (rc) return rc;
     }
   });
@@ -381,9 +381,18 @@ extern "C" PFB_API size_t pfb_corr_level_bytes(int B, int H, int W, int level, p
 
 extern "C" PFB_API int pfb_corr_volume_build(const void* fmap1, const void* fmap2, void* const* pyramid, int B, int H,
                                      int W, int C, int levels, pfb_dtype dtype, int impl, pfb_stream stream) {
+  return pfb_corr_volume_build_ex(fmap1, fmap2, pyramid, B, H, W, H, W, C, levels, 1.0f / sqrtf((float)(C > 0 ? C : 1)), dtype, impl,
+                                  stream);
+}
+
+extern "C" PFB_API int pfb_corr_volume_build_ex(const void* fmap1, const void* fmap2, void* const* pyramid, int B, int H1, int W1,
+                                                int H, int W, int C, int levels, float scale, pfb_dtype dtype, int impl,
+                                                pfb_stream stream) {
   PFB_CHECK_ARG(fmap1 && fmap2 && pyramid, "corr_volume_build: null pointer");
   PFB_CHECK_ARG(dtype_ok(dtype), "corr_volume_build: bad dtype %d", (int)dtype);
-  PFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "corr_volume_build: bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
+  PFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && H1 > 0 && W1 > 0 && C > 0, "corr_volume_build: bad shape B=%d queries %dx%d targets %dx%d C=%d", B,
+                H1, W1, H, W, C);
+  const int N1 = H1 * W1;
   PFB_CHECK_ARG(levels >= 1 && levels <= PFB_MAX_LEVELS, "corr_volume_build: levels=%d out of range", levels);
   PFB_CHECK_ARG((H >> (levels - 1)) >= 1 && (W >> (levels - 1)) >= 1,
                 "corr_volume_build: %dx%d grid too small for %d levels", H, W, levels);
@@ -394,8 +403,8 @@ extern "C" PFB_API int pfb_corr_volume_build(const void* fmap1, const void* fmap
     set_error("corr_volume_build: tcgen05 path does not support B=%d H=%d W=%d C=%d dtype=%d", B, H, W, C, (int)dtype);
     return PFB_ERR_UNSUPPORTED;
   }
-  if ((impl == 0 && can_umma) || impl == 2) return corr_volume_umma(fmap1, fmap2, pyramid, B, H, W, C, levels, dtype, s);
-  return corr_volume_simt(fmap1, fmap2, pyramid, B, H, W, C, levels, dtype, s);
+  if ((impl == 0 && can_umma) || impl == 2) return corr_volume_umma(fmap1, fmap2, pyramid, B, N1, H, W, C, levels, scale, dtype, s);
+  return corr_volume_simt(fmap1, fmap2, pyramid, B, N1, H, W, C, levels, scale, dtype, s);
 }
 
 extern "C" PFB_API int pfb_avg_pool2x2_nhwc(const void* in, void* out, int N, int H, int W, int C, pfb_dtype dtype,
@@ -442,7 +451,15 @@ static int launch_lookup_t(const LevelTable& lv, const float* coords, void* out,
 extern "C" PFB_API int pfb_corr_lookup(void* const* pyramid, const float* coords, void* out, int B, int H, int W,
                                int levels, int radius, pfb_dtype dtype, pfb_dtype out_dtype, int out_nchw,
                                int out_stride, pfb_stream stream) {
+  return pfb_corr_lookup_ex(pyramid, nullptr, nullptr, coords, out, B, H, W, levels, radius, dtype, out_dtype, out_nchw, out_stride,
+                            stream);
+}
+
+extern "C" PFB_API int pfb_corr_lookup_ex(void* const* pyramid, const int* level_h, const int* level_w, const float* coords, void* out,
+                                          int B, int H, int W, int levels, int radius, pfb_dtype dtype, pfb_dtype out_dtype,
+                                          int out_nchw, int out_stride, pfb_stream stream) {
   PFB_CHECK_ARG(pyramid && coords && out, "corr_lookup: null pointer");
+  PFB_CHECK_ARG((level_h == nullptr) == (level_w == nullptr), "corr_lookup: level_h and level_w come together");
   PFB_CHECK_ARG(dtype_ok(dtype) && dtype_ok(out_dtype), "corr_lookup: bad dtype");
   PFB_CHECK_ARG(B > 0 && H > 0 && W > 0, "corr_lookup: bad shape");
   PFB_CHECK_ARG(levels >= 1 && levels <= PFB_MAX_LEVELS, "corr_lookup: levels=%d out of range", levels);
@@ -450,7 +467,7 @@ extern "C" PFB_API int pfb_corr_lookup(void* const* pyramid, const float* coords
   const int planes = levels * (2 * radius + 1) * (2 * radius + 1);
   PFB_CHECK_ARG(out_nchw || out_stride >= planes, "corr_lookup: out_stride=%d < %d planes", out_stride, planes);
   LevelTable lv;
-  int rc = fill_levels(lv, pyramid, H, W, levels);
+  int rc = fill_levels(lv, pyramid, H, W, levels, level_h, level_w);
   PFB_CHECK_ARG(rc == 0, "corr_lookup: pyramid level missing or empty (rc=%d)", rc);
   PFB_DISPATCH_DTYPE(dtype, T, {
     return launch_lookup_t<T>(lv, coords, out, B * H * W, H * W, levels, radius, out_dtype, out_nchw, out_stride,

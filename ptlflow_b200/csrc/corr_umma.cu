@@ -253,9 +253,9 @@ bool corr_volume_umma_supported(int B, int H, int W, int C, int L, pfb_dtype dt)
   return true;
 }
 
-int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, int H, int W, int C, int L, pfb_dtype dt,
-                     cudaStream_t s) {
-  const int N = H * W;
+int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, int N1, int H, int W, int C, int L, float scale,
+                     pfb_dtype dt, cudaStream_t s) {
+  const int N = N1;  // queries; targets are the H x W grid (equal to the query grid for RAFT, its own for SEA-RAFT levels)
   const int kchunks = C / 64;
   CUtensorMap tmA, tmB;
   {
@@ -294,7 +294,6 @@ int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, in
   if (groups < 1) groups = 1;
   if (groups > n_tiles) groups = n_tiles;
   const size_t smem = (size_t)3 * kchunks * kTileBytes + (tma_store ? 8 * 128 * 32 : 0) + sizeof(CorrBars) + 1024;
-  const float scale = 1.0f / sqrtf((float)C);
   dim3 grid(m_tiles, groups, B);
   ProfScope prof(KC_VOLUME, s);
   if (dt == PFB_F16) {

@@ -275,9 +275,12 @@ extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void*
   // measured on B200 (launch lists, 16 frames): 1536 px/block for the 220x512 maps, 768 for 110x256 (53 / 27 us vs 57 / 31 at 1024)
   const int ppb = env_ppb > 0 && HW >= 8192 ? env_ppb : (HW >= 65536 ? 1536 : (HW >= 8192 ? 768 : (HW >= 1024 ? 256 : 64)));
   dim3 grid(ceil_div(HW, ppb), B);
-  ProfScope prof(KC_MISC, s);
-  PFB_DISPATCH_DTYPE(dtype, T, { inorm_stats_kernel<T><<<grid, threads, 2 * C * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb); });
+  {
+    ProfScope prof(KC_ENC_STATS, s);
+    PFB_DISPATCH_DTYPE(dtype, T, { inorm_stats_kernel<T><<<grid, threads, 2 * C * sizeof(float), s>>>((const T*)x, stats, HW, C, ppb); });
+  }
   PFB_LAUNCH_CHECK();
+  ProfScope prof(KC_ENC_AFFINE, s);
   PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, stats, nullptr, residual, y, B, HW, C, eps, relu, s); });
   return PFB_OK;
 }
@@ -292,7 +295,7 @@ extern "C" PFB_API int pfb_instance_norm_apply(const void* x, void* y, const voi
   cudaStream_t s = as_stream(stream);
   const int HW = H * W;
   double* stats = reinterpret_cast<double*>(workspace);
-  ProfScope prof(KC_MISC, s);
+  ProfScope prof(KC_ENC_AFFINE, s);
   PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, stats, nullptr, residual, y, B, HW, C, eps, relu, s); });
   return PFB_OK;
 }
@@ -305,7 +308,7 @@ extern "C" PFB_API int pfb_bias_act(const void* x, const float* bias, const void
   PFB_CHECK_ARG(B <= 65535, "bias_act: batch too large");
   cudaStream_t s = as_stream(stream);
   (void)workspace;
-  ProfScope prof(KC_MISC, s);
+  ProfScope prof(KC_ENC_AFFINE, s);
   PFB_DISPATCH_DTYPE(dtype, T, { return launch_affine<T>(x, nullptr, bias, residual, y, B, H * W, C, 0.f, relu, s); });
   return PFB_OK;
 }

@@ -484,7 +484,7 @@ extern "C" PFB_API int pfb_first_conv7x7s2(const void* x, const void* wpack, con
   a.relu = relu;
   a.ab_fmt = dtype == PFB_F16 ? 0 : 1;
   const size_t smem = kFcABytes + kFcSlots * kFcSlotBytes + 16 * 2048 + sizeof(FcBars) + 1024;
-  ProfScope prof(KC_MISC, s);  // encoder side: not part of the update-block conv roofline
+  ProfScope prof(KC_ENC_CONV1, s);  // encoder side: not part of the update-block conv roofline
   if (dtype == PFB_F16) {
     PFB_CUDA(cudaFuncSetAttribute(first_conv_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFB_CUDA(launch_pdl(first_conv_umma_kernel<__half>, dim3(grid), dim3(576), smem, s, a));
@@ -515,7 +515,7 @@ extern "C" PFB_API int pfb_flow_conv7x7(const float* flow, const void* wpack, co
   grid = ceil_div(a.n_items, a.per_cta);
   a.ab_fmt = dtype == PFB_F16 ? 0 : 1;
   const size_t smem = kFlABytes + 2 * kFlSlotBytes + 8 * 2048 + sizeof(FlBars) + 1024;
-  ProfScope prof(KC_CONV, s);
+  ProfScope prof(KC_FLOWCONV, s);
   if (dtype == PFB_F16) {
     PFB_CUDA(cudaFuncSetAttribute(flow_conv7x7_umma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFB_CUDA(launch_pdl(flow_conv7x7_umma_kernel<__half>, dim3(grid), dim3(448), smem, s, a));

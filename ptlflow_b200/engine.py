@@ -93,6 +93,9 @@ class RaftEngine:
             self.weights.layers[k] = v.layer_struct()
         self._workspaces: Dict[Tuple, torch.Tensor] = {}
         self.signature = self.param_signature(update_block)
+        # the pack kernels ran on the constructing thread's stream; other streams / host threads (pipeline slots) may use
+        # the packed weights as soon as the engine is published, so finish them first (one-time cost)
+        torch.cuda.current_stream(device).synchronize()
 
     # -- cache invalidation --------------------------------------------------------------------
     @staticmethod
@@ -105,7 +108,21 @@ class RaftEngine:
                             self.hidden_dim, self.context_dim, iters, int(alternate_corr), out_hw[0], out_hw[1], pad[0], pad[1],
                             self.impl)
 
-    def workspace(self, cfg: _lib.RaftCfg) -> torch.Tensor:
+    def build_volume(self, fmap1: torch.Tensor, fmap2: torch.Tensor, impl: int = 0):
+        """a1 + a2 for the refinement loop of this engine (layout chosen by the library, see refine())."""
+        return ops.corr_volume_build(fmap1, fmap2, self.corr_levels, impl=impl)
+
+    def workspace(self, cfg: _lib.RaftCfg, scratch: Optional[dict] = None) -> torch.Tensor:
+        if scratch is not None:
+            # the caller owns the scratch memory (a CUDA graph keeps the workspace it was captured with alive)
+            key = ("raft_ws", cfg.B, cfg.H, cfg.W)
+            ws = scratch.get(key)
+            if ws is None:
+                nbytes = load().pfb_raft_workspace_bytes(C.byref(cfg))
+                if nbytes == 0:
+                    check(-1, "raft_workspace_bytes")
+                ws = scratch[key] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            return ws
         # one workspace per CUDA stream (batches in flight on different streams must not share scratch memory,
         # ptlflow_b200/pipeline.py) and, per stream, one shape resident (bounded memory, SURVEY appendix B.7)
         sid = torch.cuda.current_stream(self.device).cuda_stream
@@ -116,18 +133,22 @@ class RaftEngine:
             if nbytes == 0:
                 check(-1, "raft_workspace_bytes")
             ent = (key, torch.empty(nbytes, dtype=torch.uint8, device=self.device))
-            if len(self._workspaces) >= 8:  # streams come and go: do not grow without bound
+            if len(self._workspaces) >= 8:
+                # streams come and go: do not grow without bound.  A dropped tensor returns to torch's caching allocator,
+                # which keeps the block reserved for the stream it was allocated on until that stream's queued work is
+                # done -- an evicted workspace with work still in flight is therefore not reused under that work.
                 self._workspaces.pop(next(iter(self._workspaces)))
             self._workspaces[sid] = ent
         return ent[1]
 
     def refine(self, pyramid: Sequence[torch.Tensor], net: torch.Tensor, inp: torch.Tensor, coords: torch.Tensor,
-               iters: int, out_hw, pad, fmap1: Optional[torch.Tensor] = None, attention: Optional[torch.Tensor] = None):
+               iters: int, out_hw, pad, fmap1: Optional[torch.Tensor] = None, attention: Optional[torch.Tensor] = None,
+               scratch: Optional[dict] = None):
         """Runs the loop in place on (net, coords); returns (flow_up fp32 [B,2,oh,ow], flow_small fp32 [B,2,H,W])."""
         B, H, W, _ = net.shape
         alt = fmap1 is not None
         cfg = self.make_cfg(B, H, W, iters, out_hw, pad, alt, fmap1.shape[-1] if alt else 0)
-        ws = self.workspace(cfg)
+        ws = self.workspace(cfg, scratch)
         flow_up = torch.empty((B, 2, out_hw[0], out_hw[1]), dtype=torch.float32, device=self.device)
         flow_small = torch.empty((B, 2, H, W), dtype=torch.float32, device=self.device)
         pyr = ptr_array(pyramid)

@@ -111,13 +111,17 @@ class BaseModel(LightningModule):
     # -- evaluation plumbing (validate.py / test.py call these) ------------------------------
     def validation_step(self, batch: Dict[str, Any], batch_idx: int = 0, dataloader_idx: int = 0) -> Dict[str, Any]:
         """forward + warm-start bookkeeping (base_model.py:366-430) + end-point error when ground truth is there."""
+        # ordering of base_model.py:396-430: prev_preds goes into the forward unconditionally; AFTER the forward it is
+        # dropped when this batch starts a sequence and replaced by this batch's (detached) predictions otherwise
         if self.warm_start:
-            if batch_idx == 0 or (batch.get("meta") and batch["meta"].get("is_seq_start", [False])[0]):
-                self.prev_preds = None
             batch = dict(batch, prev_preds=self.prev_preds)
         preds = self(batch)
         if self.warm_start:
-            self.prev_preds = {"flow_small": preds.get("flow_small")}
+            meta = batch.get("meta") or {}
+            if "is_seq_start" in meta and meta["is_seq_start"][0]:
+                self.prev_preds = None
+            else:
+                self.prev_preds = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in preds.items()}
         out = {"preds": preds}
         if "flows" in batch:
             gt = batch["flows"].to(preds["flows"].device, torch.float32)

@@ -4,6 +4,7 @@ ptlflow/models/raft/extractor.py:122-267 so checkpoints load strictly)."""
 from __future__ import annotations
 
 import os
+import threading
 
 import torch
 import torch.nn as nn
@@ -88,6 +89,7 @@ def _fold(conv: nn.Conv2d, norm: nn.Module, dtype, device):
 
 
 _NATIVE_CONV1 = bool(int(os.environ.get("PFB_NATIVE_CONV1", "1")))
+_prep_lock = threading.Lock()
 
 
 def _conv_pm(x: torch.Tensor, wb, stride: int, padding: int) -> torch.Tensor:
@@ -135,6 +137,13 @@ class _Encoder(nn.Module):
         cache = getattr(self, "_prep_cache", None)
         if cache is not None and cache[0] == sig:
             return cache[1]
+        with _prep_lock:  # several pipeline slots (host threads, streams) may arrive here together
+            cache = getattr(self, "_prep_cache", None)
+            if cache is not None and cache[0] == sig:
+                return cache[1]
+            return self._prepare_locked(sig, dtype, device)
+
+    def _prepare_locked(self, sig, dtype, device):
         prep = {"conv1": _fold(self.conv1, self.norm1, dtype, device), "conv2": _fold(self.conv2, nn.Identity(), dtype, device), "blocks": []}
         for layer in (self.layer1, self.layer2, self.layer3):
             for blk in layer:
@@ -145,6 +154,12 @@ class _Encoder(nn.Module):
                 if blk.downsample is not None:
                     e["down"] = _fold(blk.downsample[0], blk.downsample[1], dtype, device)
                 prep["blocks"].append(e)
+        if (_NATIVE_CONV1 and tuple(self.conv1.weight.shape) == (64, 3, 7, 7) and dtype in (torch.float16, torch.bfloat16)
+                and self.norm_fn in ("instance", "batch", "none")):
+            folded = _fold(self.conv1, self.norm1, torch.float32, device)
+            prep["conv1_native"] = (ops.pack_first_conv(folded[0], dtype), folded[1])
+        # the fold / pack kernels ran on this thread's stream: finish them before other streams can see the cache
+        torch.cuda.current_stream(device).synchronize()
         self._prep_cache = (sig, prep)
         return prep
 
@@ -164,14 +179,11 @@ class _Encoder(nn.Module):
             return ops.bias_act(y, wb[1], relu=relu, residual=residual, out=y)
 
         c1 = prep["conv1"]
-        native_c1 = (_NATIVE_CONV1 and x.shape[-1] == 4 and tuple(self.conv1.weight.shape) == (64, 3, 7, 7) and x.dtype in (torch.float16, torch.bfloat16)
+        native_c1 = ("conv1_native" in prep and x.shape[-1] == 4 and tuple(self.conv1.weight.shape) == (64, 3, 7, 7) and x.dtype in (torch.float16, torch.bfloat16)
                      and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0)
         if native_c1:
             # tcgen05 first convolution (csrc/first_conv.cu): statistics of the instance norm come out of its epilogue,
             # bias + ReLU of the folded batch norm are applied in it
-            if "conv1_native" not in prep:
-                folded = _fold(self.conv1, self.norm1, torch.float32, x.device)
-                prep["conv1_native"] = (ops.pack_first_conv(folded[0], x.dtype), folded[1])
             wpack, bias = prep["conv1_native"]
             if inst:
                 ws = ops.instance_norm_workspace((x.shape[0], 0, 0, 64), x.device)

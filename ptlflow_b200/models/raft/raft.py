@@ -95,6 +95,12 @@ class RAFT(BaseModel):
         # cuDNN runs its own NHWC channel-padding kernel in front of the 7x7 convolution (ncu launch list r01 v15)
         self.frame_channels = int(_os.environ.get("PFB_FRAME_CHANNELS", "4"))
         self._engine: Optional[RaftEngine] = None
+        # one CUDA graph per (input shape, dtype, iters, stream): PFB_CUDA_GRAPH=0 or model.use_cuda_graph = False -> eager launches
+        self.use_cuda_graph = bool(int(_os.environ.get("PFB_CUDA_GRAPH", "1")))
+        self._graphs: Dict[tuple, tuple] = {}
+        self._graph_sig = None
+        self.graph_replays = 0
+        self.graph_launches_replayed = 0  # this library's kernel launches replayed from graphs (bench.py: gpu_launches)
         self._build_networks()
 
     def _build_networks(self) -> None:
@@ -145,8 +151,129 @@ class RAFT(BaseModel):
         strict = frames.dtype == torch.float32 and self.strict_fp32
         with _cudnn_flags(self.cudnn_benchmark, not strict):
             fmaps = run(self.fnet, frames)
-            cnet = run(self.cnet, frames[:B])
+            cnet32 = self.__dict__.get("_cnet_fp32")
+            if cnet32 is None or frames.dtype == torch.float32:
+                cnet = run(self.cnet, frames[:B])
+        if cnet32 is not None and frames.dtype != torch.float32:
+            # accuracy mode (enable_fp32_context): the context encoder in true fp32, its output rounded once to the storage type
+            with _cudnn_flags(self.cudnn_benchmark, False):
+                cnet = run(cnet32, frames[:B].float()).to(frames.dtype)
         return fmaps[:B], fmaps[B:], cnet
+
+    def enable_fp32_context(self, on: bool = True) -> "RAFT":
+        """Accuracy mode for f16 / bf16 models: evaluate the context encoder in true fp32 (weights as they are NOW, so call
+        this before ``.half()``), everything else unchanged.  tools/f16_error_budget.py shows why this is the one stage that
+        matters: its output (``net0`` / ``inp``) enters every refinement iteration, so its f16 operand rounding is a static
+        perturbation that never averages out (> 90 % of the half-precision flow error); with it in fp32 the f16 pipeline
+        is within north_star's 1e-2 px of the fp32 reference.  Costs a cuDNN fp32 pass over 1/3 of the encoder work, which
+        is why it is not the default (bench.py reports both)."""
+        import copy
+
+        if on:
+            c = copy.deepcopy(self.cnet).float().eval()
+            for p_ in c.parameters():
+                p_.requires_grad_(False)
+            self.__dict__["_cnet_fp32"] = c  # not a registered submodule: .half() / state_dict() / parameters() do not see it
+        else:
+            self.__dict__.pop("_cnet_fp32", None)
+        self._graphs.clear()
+        return self
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        c = self.__dict__.get("_cnet_fp32")
+        if c is not None:  # follow device moves, keep fp32
+            dev = next(self.parameters()).device
+            c.to(device=dev)
+            self._graphs.clear()
+        return out
+
+    def _forward_device(self, images: torch.Tensor, flow_init: Optional[torch.Tensor], scratch: Optional[dict] = None):
+        """images [B,2,3,H,W] on the device (only read) -> (flow_up fp32 [B,2,H,W], flow_small fp32 [B,2,H/8,W/8]).
+        Everything in here is enqueued on the current stream with no host synchronisation and no data-dependent
+        control flow, so the whole forward can be captured into one CUDA graph (``_forward_graphed``)."""
+        from ...utils.utils import InputPadder
+
+        # fused equivalent of preprocess_images(bgr_add=-0.5, bgr_mult=2, bgr_to_rgb=True, pad "replicate" two-sided)
+        # (raft.py:127-135): one kernel, output already pixel-major; the caller's tensor is only read
+        resizer = InputPadder(images.shape, stride=self.output_stride, pad_mode="replicate", two_side_pad=True)
+        B = images.shape[0]
+        frames = ops.preprocess_frames(images, resizer.tgt_size, resizer.pad_top_left, out_channels=self.frame_channels)
+        fmap1, fmap2, cnet = self._encode(frames, B)
+        _, H8, W8, _ = fmap1.shape
+        eng = self._get_engine(fmap1.dtype, fmap1.device)
+        net, inp = ops.context_split(cnet, self.hidden_dim, self.context_dim)
+        coords = ops.init_coords(B, H8, W8, fmap1.device, flow_init)
+
+        if self.alternate_corr:
+            pyramid, f1 = ops.feature_pyramid(fmap2, self.corr_levels), fmap1
+        else:
+            pyramid, f1 = eng.build_volume(fmap1, fmap2, impl=self.kernel_impl), None
+
+        orig_h, orig_w = images.shape[-2:]
+        pad_top, pad_left = resizer.pad_top_left
+        attention = self._attention(inp, eng)  # gma only (gma.py:181)
+        flow_up, flow_small = eng.refine(pyramid, net, inp, coords, self.iters, (orig_h, orig_w), (pad_top, pad_left), fmap1=f1,
+                                         attention=attention, scratch=scratch)
+        return self.postprocess_predictions(flow_up, resizer, is_flow=True), flow_small  # un-pad is a no-op: written un-padded
+
+    # -- CUDA graph of the whole forward (SURVEY.md section 7 step 9, appendix B.9) ------------------------------
+    def _graph_key(self, images: torch.Tensor, flow_init) -> tuple:
+        sid = torch.cuda.current_stream(images.device).cuda_stream  # one graph (and one set of static buffers) per stream
+        return (tuple(images.shape), images.dtype, str(images.device), sid, self.iters, bool(self.alternate_corr), flow_init is not None,
+                self.kernel_impl, self.corr_levels, self.corr_radius, self.encoder_chunk, self.frame_channels)
+
+    def _weights_signature(self) -> tuple:
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple((b.data_ptr(), b._version) for b in self.buffers())
+
+    def _forward_graphed(self, images: torch.Tensor, flow_init: Optional[torch.Tensor]):
+        """One ``cudaGraphLaunch`` per forward.  The ~250 kernels of a forward (encoders, volume, 12 x 13 refinement
+        launches, upsample) cost ~6 ms of host time when launched one by one; captured once per
+        (shape, dtype, iters, stream) they replay from static buffers.  The parameters' storage/version is part of the
+        key, so ``load_state_dict`` / ``.half()`` after a capture re-captures."""
+        sig = self._weights_signature()
+        if self._graph_sig != sig:
+            self._graphs.clear()
+            self._graph_sig = sig
+        key = self._graph_key(images, flow_init)
+        ent = self._graphs.get(key)
+        dev = images.device
+        if ent is None:
+            cur = torch.cuda.current_stream(dev)
+            static_in = torch.empty_like(images)
+            static_init = torch.empty_like(flow_init) if flow_init is not None else None
+            static_in.copy_(images)
+            if static_init is not None:
+                static_init.copy_(flow_init)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            from ... import _lib
+
+            lib = _lib.load()
+            scratch: dict = {}  # workspaces of this graph: owned by the cache entry, so they live exactly as long as the graph
+            with torch.cuda.stream(side):
+                for _ in range(2):  # eager warm-up on the capture stream: cuDNN autotune, weight packing, scratch caches
+                    self._forward_device(static_in, static_init, scratch)
+                side.synchronize()
+                n0 = lib.pfb_launch_count(-1)
+                graph = torch.cuda.CUDAGraph()
+                # thread_local: other host threads (pipeline slots, data loaders) keep making CUDA calls while this one captures
+                with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                    flow_up, flow_small = self._forward_device(static_in, static_init, scratch)
+                launches = int(lib.pfb_launch_count(-1) - n0)
+            cur.wait_stream(side)
+            if len(self._graphs) >= 8:  # shapes / streams come and go (infer.py, validate.py: dataset-dependent sizes)
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = (graph, static_in, static_init, flow_up, flow_small, launches, scratch)
+            self._graphs[key] = ent
+        graph, static_in, static_init, flow_up, flow_small, launches = ent[:6]
+        static_in.copy_(images, non_blocking=True)
+        if static_init is not None:
+            static_init.copy_(flow_init, non_blocking=True)
+        graph.replay()
+        self.graph_replays += 1
+        self.graph_launches_replayed += launches
+        return flow_up, flow_small
 
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Estimate optical flow between a pair of frames (eval semantics of raft.py:125-194)."""
@@ -155,42 +282,24 @@ class RAFT(BaseModel):
             raise RuntimeError("ptlflow_b200 runs on CUDA (sm_100a) only: move the model and inputs to the GPU. There is no CPU path.")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.update_block.parameters()) and self.training:
             raise NotImplementedError("ptlflow_b200 implements the inference hot path; call under torch.no_grad() / model.eval()")
-        with torch.no_grad():
-            # fused equivalent of preprocess_images(bgr_add=-0.5, bgr_mult=2, bgr_to_rgb=True, pad "replicate" two-sided)
-            # (raft.py:127-135): one kernel, output already pixel-major; the caller's tensor is only read
-            from ...utils.utils import InputPadder
-
+        with torch.no_grad(), torch.cuda.device(images.device):
             images = images.contiguous()
-            resizer = InputPadder(images.shape, stride=self.output_stride, pad_mode="replicate", two_side_pad=True)
-            B = images.shape[0]
-            frames = ops.preprocess_frames(images, resizer.tgt_size, resizer.pad_top_left, out_channels=self.frame_channels)
-            fmap1, fmap2, cnet = self._encode(frames, B)
-            _, H8, W8, _ = fmap1.shape
-            eng = self._get_engine(fmap1.dtype, fmap1.device)
-            net, inp = ops.context_split(cnet, self.hidden_dim, self.context_dim)
-
             flow_init = None
             prev = inputs.get("prev_preds")
             if prev is not None and prev.get("flow_small") is not None:
                 from ...utils.warm_start import forward_interpolate_batch
 
-                flow_init = forward_interpolate_batch(prev["flow_small"])
-            coords = ops.init_coords(B, H8, W8, fmap1.device, flow_init)
-
-            if self.alternate_corr:
-                pyramid, f1 = ops.feature_pyramid(fmap2, self.corr_levels), fmap1
+                flow_init = forward_interpolate_batch(prev["flow_small"]).to(device=images.device, dtype=torch.float32).contiguous()
+            use_graph = self.use_cuda_graph and not torch.cuda.is_current_stream_capturing()
+            if use_graph:
+                flow_up, flow_small = self._forward_graphed(images, flow_init)
             else:
-                pyramid, f1 = ops.corr_volume_build(fmap1, fmap2, self.corr_levels, impl=self.kernel_impl), None
-
-            orig_h, orig_w = inputs["images"].shape[-2:]
-            pad_top, pad_left = resizer.pad_top_left
-            attention = self._attention(inp, eng)  # gma only (gma.py:181)
-            flow_up, flow_small = eng.refine(pyramid, net, inp, coords, self.iters, (orig_h, orig_w), (pad_top, pad_left), fmap1=f1,
-                                             attention=attention)
-            flow_up = self.postprocess_predictions(flow_up, resizer, is_flow=True)  # no-op: written un-padded
+                flow_up, flow_small = self._forward_device(images, flow_init)
             out_dtype = inputs["images"].dtype
-            return {"flows": flow_up.to(out_dtype)[:, None], "flow_small": flow_small.to(out_dtype),
-                    "flows_fp32": flow_up[:, None]}
+            # .to() / clone() give the caller fresh tensors: the graph's static outputs are overwritten by the next replay
+            flows = flow_up.to(out_dtype) if out_dtype != torch.float32 else (flow_up.clone() if use_graph else flow_up)
+            small = flow_small.to(out_dtype) if out_dtype != torch.float32 else (flow_small.clone() if use_graph else flow_small)
+            return {"flows": flows[:, None], "flow_small": small, "flows_fp32": (flow_up.clone() if use_graph else flow_up)[:, None]}
 
 
 class RAFTSmall(RAFT):

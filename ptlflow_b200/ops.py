@@ -52,12 +52,32 @@ def corr_volume_build(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int = 4,
     return pyr
 
 
+def corr_volume_build_ex(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int = 1, scale: Optional[float] = None,
+                         impl: int = 0) -> List[torch.Tensor]:
+    """fmap1 [B,H1,W1,C] (queries), fmap2 [B,H2,W2,C] (targets, any grid) -> [level0 [B*H1*W1,H2,W2], ...]; ``scale`` defaults to
+    1/sqrt(C).  SEA-RAFT's per-level volumes (sea_raft/corr.py:77-83), FlowFormer's unscaled cost maps (encoder.py:543-561)."""
+    require_cuda(fmap1, "fmap1"); require_cuda(fmap2, "fmap2")
+    if fmap1.dim() != 4 or fmap2.dim() != 4 or fmap1.shape[0] != fmap2.shape[0] or fmap1.shape[3] != fmap2.shape[3] or fmap1.dtype != fmap2.dtype:
+        raise RuntimeError("corr_volume_build_ex: fmap1 [B,H1,W1,C] / fmap2 [B,H2,W2,C] with equal B, C and dtype")
+    B, H1, W1, Cc = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    if (H2 >> (levels - 1)) < 1 or (W2 >> (levels - 1)) < 1:
+        raise RuntimeError(f"corr_volume_build_ex: {H2}x{W2} target grid too small for {levels} levels")
+    pyr = [torch.empty((B * H1 * W1, H2 >> l, W2 >> l), dtype=fmap1.dtype, device=fmap1.device) for l in range(levels)]
+    with torch.cuda.device(fmap1.device):
+        check(load().pfb_corr_volume_build_ex(fmap1.data_ptr(), fmap2.data_ptr(), ptr_array(pyr), B, H1, W1, H2, W2, Cc, levels,
+                                              float(Cc ** -0.5 if scale is None else scale), dtype_code(fmap1.dtype), impl,
+                                              stream_ptr(fmap1.device)), "corr_volume_build_ex")
+    return pyr
+
+
 # ------------------------------------------------------------------------------------------
 # a3
 # ------------------------------------------------------------------------------------------
 def corr_lookup(pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: int, grid_hw, nchw: bool = True,
-                out_dtype: Optional[torch.dtype] = None, out_stride: Optional[int] = None) -> torch.Tensor:
-    """coords fp32 [B,H,W,2] -> [B, L*(2r+1)^2, H, W] (nchw) or [B,H,W,out_stride].  corr.py:29-54."""
+                out_dtype: Optional[torch.dtype] = None, out_stride: Optional[int] = None, level_hw=None) -> torch.Tensor:
+    """coords fp32 [B,H,W,2] -> [B, L*(2r+1)^2, H, W] (nchw) or [B,H,W,out_stride].  corr.py:29-54.
+    ``level_hw``: explicit (h, w) per level when the levels are not the floor-halved query grid."""
     require_cuda(coords, "coords")
     if coords.dtype != torch.float32:
         raise RuntimeError("corr_lookup: coords must be float32 [B,H,W,2]")
@@ -69,9 +89,16 @@ def corr_lookup(pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: i
     stride = planes if out_stride is None else out_stride
     out = torch.empty((B, planes, H, W) if nchw else (B, H, W, stride), dtype=odt, device=coords.device)
     with torch.cuda.device(coords.device):
-        check(load().pfb_corr_lookup(ptr_array(pyramid), coords.data_ptr(), out.data_ptr(), B, H, W, L, radius,
-                                     dtype_code(pyramid[0].dtype), dtype_code(odt), int(nchw), stride,
-                                     stream_ptr(coords.device)), "corr_lookup")
+        if level_hw is None:
+            check(load().pfb_corr_lookup(ptr_array(pyramid), coords.data_ptr(), out.data_ptr(), B, H, W, L, radius,
+                                         dtype_code(pyramid[0].dtype), dtype_code(odt), int(nchw), stride,
+                                         stream_ptr(coords.device)), "corr_lookup")
+        else:
+            lh = (C.c_int * L)(*[int(h) for h, _ in level_hw])
+            lw = (C.c_int * L)(*[int(w) for _, w in level_hw])
+            check(load().pfb_corr_lookup_ex(ptr_array(pyramid), lh, lw, coords.data_ptr(), out.data_ptr(), B, H, W, L, radius,
+                                            dtype_code(pyramid[0].dtype), dtype_code(odt), int(nchw), stride,
+                                            stream_ptr(coords.device)), "corr_lookup_ex")
     return out
 
 

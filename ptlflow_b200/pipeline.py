@@ -25,6 +25,18 @@ from typing import Dict, List, Optional
 import torch
 
 
+def _cuda_tensors(*objs):
+    """Every CUDA tensor inside (possibly nested) dicts / lists / tuples."""
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                yield o
+        elif isinstance(o, dict):
+            yield from _cuda_tensors(*o.values())
+        elif isinstance(o, (list, tuple)):
+            yield from _cuda_tensors(*o)
+
+
 class _Result:
     """Outputs of one submitted batch; ``get()`` waits for the slot's stream to reach the end of that batch."""
 
@@ -34,6 +46,7 @@ class _Result:
 
     def get(self) -> Dict[str, torch.Tensor]:
         out, event = self._future.result()
+        self._future = _Done((out, event))  # the Future object (also referenced by the worker's frame) lets go of the tensors
         event.synchronize()
         cur = torch.cuda.current_stream(self._device)
         for v in out.values():  # allocated on the slot's stream, consumed on the caller's
@@ -44,6 +57,14 @@ class _Result:
     def enqueued(self) -> None:
         """Returns when the host side has finished launching the batch (the GPU may still be running it)."""
         self._future.result()
+
+
+class _Done:
+    def __init__(self, value):
+        self._value = value
+
+    def result(self):
+        return self._value
 
 
 class FramePipeline:
@@ -64,7 +85,7 @@ class FramePipeline:
         self._queues: List[queue.Queue] = [queue.Queue() for _ in range(depth)]
         self._dev_in: List[Optional[torch.Tensor]] = [None] * depth
         self._next = 0
-        self._pending: List[_Result] = []
+        self._pending: List[threading.Event] = []
         self._threads = [threading.Thread(target=self._run, args=(i,), daemon=True, name=f"pfb-slot{i}") for i in range(depth)]
         for t in self._threads:
             t.start()
@@ -79,9 +100,13 @@ class FramePipeline:
                 job = q.get()
                 if job is None:
                     return
-                images, extra, host_out, ready, fut = job
+                images, extra, host_out, ready, fut, launched = job
                 try:
                     stream.wait_event(ready)  # everything the caller had enqueued before submit()
+                    # device-resident inputs were allocated on the caller's stream but are read on this one: tell the
+                    # caching allocator, or the block could be handed back (and overwritten) while the forward still reads it
+                    for t in _cuda_tensors(images, extra):
+                        t.record_stream(stream)
                     if not images.is_cuda:  # pinned host frames: H2D on this slot's stream, overlapping the other slot's compute
                         buf = self._dev_in[slot]
                         if buf is None or buf.shape != images.shape or buf.dtype != images.dtype:
@@ -97,8 +122,11 @@ class FramePipeline:
                     done = torch.cuda.Event()
                     done.record(stream)
                     fut.set_result((out, done))
+                    del out
                 except BaseException as e:  # noqa: BLE001 -- delivered to the caller through the future
                     fut.set_exception(e)
+                finally:
+                    launched.set()
 
     # -- caller side ---------------------------------------------------------------------------
     def submit(self, inputs: Dict[str, torch.Tensor], host_out: Optional[torch.Tensor] = None) -> _Result:
@@ -109,17 +137,20 @@ class FramePipeline:
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device))
         fut: Future = Future()
+        launched = threading.Event()
         extra = {k: v for k, v in inputs.items() if k != "images"}
-        self._queues[slot].put((inputs["images"], extra, host_out, ready, fut))
-        res = _Result(fut, self.device)
-        self._pending.append(res)
-        return res
+        self._queues[slot].put((inputs["images"], extra, host_out, ready, fut, launched))
+        # only the "host side has launched it" markers are kept here: the outputs live exactly as long as the caller
+        # keeps the returned _Result (a long clip must not accumulate every batch's flow on the GPU)
+        self._pending = [e for e in self._pending if not e.is_set()]
+        self._pending.append(launched)
+        return _Result(fut, self.device)
 
     def drain(self) -> None:
         """Host: wait until every submitted batch has been launched; device: make the caller's current stream wait for
         all slots (so an event recorded after drain() brackets the submitted work)."""
-        for r in self._pending:
-            r.enqueued()
+        for e in self._pending:
+            e.wait()
         self._pending.clear()
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:

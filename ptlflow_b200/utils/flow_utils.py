@@ -70,10 +70,13 @@ def _write_flo(f: IO[bytes], flow: np.ndarray) -> None:
 # ---------------------------------------------------------------------------------------------
 # KITTI .png
 # ---------------------------------------------------------------------------------------------
-def _read_png(path: PathLike, mult: float) -> np.ndarray:
+def _read_png(path, mult: float) -> np.ndarray:
     import cv2
 
-    bgr = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+    if hasattr(path, "read"):  # file object: decode from its bytes
+        bgr = cv2.imdecode(np.frombuffer(path.read(), dtype=np.uint8), cv2.IMREAD_UNCHANGED)
+    else:
+        bgr = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
     if bgr is None or bgr.ndim != 3 or bgr.shape[2] != 3 or bgr.dtype != np.uint16:
         raise ValueError(f"{path}: not a 16-bit 3-channel flow png")
     rgb = bgr[..., ::-1]
@@ -82,7 +85,7 @@ def _read_png(path: PathLike, mult: float) -> np.ndarray:
     return flow
 
 
-def _write_png(path: PathLike, flow: np.ndarray, mult: float) -> None:
+def _write_png(path, flow: np.ndarray, mult: float) -> None:
     import cv2
 
     valid = ~np.isnan(flow).any(axis=-1)
@@ -90,8 +93,15 @@ def _write_png(path: PathLike, flow: np.ndarray, mult: float) -> None:
     enc = np.empty(flow.shape[:2] + (3,), dtype=np.uint16)
     enc[..., :2] = (uv * mult + 2**15).astype(np.uint16)
     enc[..., 2] = valid
-    if not cv2.imwrite(str(path), np.ascontiguousarray(enc[..., ::-1])):
-        raise OSError(f"could not write {path}")
+    # always through the '.png' encoder (a '.png128' suffix has no cv2 writer); file objects get the encoded bytes
+    ok, buf = cv2.imencode(".png", np.ascontiguousarray(enc[..., ::-1]))
+    if not ok:
+        raise OSError(f"could not encode {path} as png")
+    if hasattr(path, "write"):
+        path.write(buf.tobytes())
+    else:
+        with open(path, "wb") as f:
+            f.write(buf.tobytes())
 
 
 # ---------------------------------------------------------------------------------------------

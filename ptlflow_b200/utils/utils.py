@@ -96,3 +96,23 @@ def bgr_val_as_tensor(val, reference: torch.Tensor, position: int = -3) -> torch
         shape[position] = 3
         val = val.reshape(shape)
     return val
+
+
+def count_parameters(model: torch.nn.Module) -> int:
+    """Trainable parameters (ptlflow/utils/utils.py:262-277; 5 257 536 for raft, the model_benchmark.py column)."""
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+def tensor_dict_to_numpy(tensor_dict, padder: Optional[InputPadder] = None):
+    """Every tensor of the dict -> numpy HWC of its first sample / first frame (ptlflow/utils/utils.py:331-361)."""
+    out = {}
+    for k, v in tensor_dict.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().float().cpu()
+            if padder is not None:
+                v = padder.unfill(v)
+            while v.dim() > 3:
+                v = v[0]
+            v = v.permute(1, 2, 0).numpy()
+        out[k] = v
+    return out

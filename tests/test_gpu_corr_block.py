@@ -1,0 +1,112 @@
+"""The corr-block protocol on the GPU (ptlflow/models/raft/corr.py:104-118):
+``get_corr_block(fmap1, fmap2, num_levels, radius, alternate_corr)`` built from the reference's NCHW tensors, called with
+``coords [B,2,H,W]``, returning ``[B, L*(2r+1)^2, H, W]`` contiguous in coords' dtype -- against the vectors the
+reference's own CorrBlock / IterativeCorrBlock wrote (tests/golden/op_corr_lookup.npz, op_alt_corr.npz).
+This is the seam the sibling ``corr.py`` copies bind to (appendix E): also exercised here are the single-level r = 4
+lookup of the FlowFormer decoder (flowformer/decoder.py:262-280) and SEA-RAFT's per-level volumes against a separately
+sized target grid (sea_raft/corr.py:77-83)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import load_golden
+from oracle import raft_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _fmaps(recipe):
+    b, c, h, w = recipe["b"], recipe["c"], recipe["h"], recipe["w"]
+    f1 = torch.from_numpy(synth.synth_normal("ops/fmap1", (b, c, h, w), recipe["seed"]))
+    f2 = torch.from_numpy(synth.synth_normal("ops/fmap2", (b, c, h, w), recipe["seed"]))
+    return f1, f2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-5), (torch.float16, 4e-2)])
+@pytest.mark.parametrize("memory_format", [torch.contiguous_format, torch.channels_last])
+def test_corr_block_against_reference_vectors(dtype, tol, memory_format):
+    from ptlflow_b200.models.raft.corr import CorrBlock, get_corr_block
+
+    recipe, g = load_golden("op_corr_lookup")
+    f1, f2 = _fmaps(recipe)
+    f1 = f1.to(DEV, dtype).contiguous(memory_format=memory_format)
+    f2 = f2.to(DEV, dtype).contiguous(memory_format=memory_format)
+    corr_fn = get_corr_block(f1, f2, num_levels=recipe["levels"], radius=recipe["radius"], alternate_corr=False)
+    assert isinstance(corr_fn, CorrBlock)
+    coords = torch.from_numpy(g["coords"]).to(DEV, dtype)  # the reference hands coords in the model dtype (raft.py:106)
+    out = corr_fn(coords)
+    assert out.shape == g["lookup"].shape and out.dtype == dtype and out.is_contiguous()
+    # f16 coordinates are quantised by the CALLER here (0.03-0.06 px at x ~ 100): compare with the oracle at the same coords
+    ref = O.corr_lookup(O.corr_pyramid(O.corr_volume(*_fmaps(recipe)), recipe["levels"]), coords.float().cpu(), recipe["radius"])
+    assert (out.float().cpu() - ref).abs().max().item() < tol
+    if dtype == torch.float32:
+        assert np.abs(out.cpu().numpy() - g["lookup"]).max() < tol
+    out2 = corr_fn(coords + 0.5)  # constructed once, called `iters` times
+    assert (out2 - out).abs().max().item() > 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-5), (torch.float16, 4e-2)])
+def test_alternate_corr_block_against_reference_vectors(dtype, tol):
+    from ptlflow_b200.models.raft.corr import AlternateCorrBlock, get_corr_block
+
+    recipe, g = load_golden("op_alt_corr")
+    f1, f2 = _fmaps(recipe)
+    corr_fn = get_corr_block(f1.to(DEV, dtype), f2.to(DEV, dtype), num_levels=recipe["levels"], radius=recipe["radius"], alternate_corr=True)
+    assert isinstance(corr_fn, AlternateCorrBlock)
+    coords = torch.from_numpy(g["coords"]).to(DEV, dtype)
+    out = corr_fn(coords)
+    assert out.shape == g["lookup"].shape and out.dtype == dtype
+    ref = O.alt_corr_lookup(f1, f2, coords.float().cpu(), recipe["radius"], recipe["levels"])
+    assert (out.float().cpu() - ref).abs().max().item() < tol
+    if dtype == torch.float32:
+        assert np.abs(out.cpu().numpy() - g["lookup"]).max() < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-5), (torch.bfloat16, 2e-1)])
+def test_flowformer_single_level_lookup(dtype, tol):
+    """FlowFormer's encode_flow_token (decoder.py:262-280): ONE level, r = 4, cost maps WITHOUT the 1/sqrt(C) scale
+    (encoder.py:543-561) -- the same kernels with levels = 1 and scale = 1."""
+    from ptlflow_b200 import ops
+
+    b, c, h, w = 1, 64, 27, 40  # odd sizes: no tensor-core tile divides them
+    f1 = torch.from_numpy(synth.synth_normal("ff/f1", (b, c, h, w), 3))
+    f2 = torch.from_numpy(synth.synth_normal("ff/f2", (b, c, h, w), 3))
+    coords = O.coords_grid(b, h, w) + torch.from_numpy(synth.synth_normal("ff/c", (b, 2, h, w), 3, scale=6.0))
+    pm = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)  # noqa: E731
+    (cost,) = ops.corr_volume_build_ex(pm(f1), pm(f2), levels=1, scale=1.0)
+    assert cost.shape == (b * h * w, h, w)
+    look = ops.corr_lookup([cost], coords.permute(0, 2, 3, 1).contiguous().to(DEV), 4, (h, w), nchw=True, out_dtype=torch.float32)
+    vol = O.corr_volume(f1, f2) * (c ** 0.5)
+    ref = O.corr_lookup([vol], coords, 4)
+    assert look.shape == (b, 81, h, w)
+    assert (look.cpu() - ref).abs().max().item() < tol * (c ** 0.5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-5), (torch.float16, 4e-2)])
+def test_sea_raft_pyramid_of_volumes(dtype, tol):
+    """SEA-RAFT style pyramid (sea_raft/corr.py:77-83): one all-pairs product PER LEVEL of the full-resolution fmap1 against
+    fmap2 halved by bilinear interpolation (align_corners=False), instead of average-pooling the volume; same lookup."""
+    from ptlflow_b200 import ops
+
+    b, c, h, w = 2, 128, 24, 40
+    f1 = torch.from_numpy(synth.synth_normal("sea/f1", (b, c, h, w), 4))
+    f2 = torch.from_numpy(synth.synth_normal("sea/f2", (b, c, h, w), 4))
+    coords = O.coords_grid(b, h, w) + torch.from_numpy(synth.synth_normal("sea/c", (b, 2, h, w), 4, scale=4.0))
+    pm = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)  # noqa: E731
+    pyr, ref_pyr, t2 = [], [], f2
+    for lvl in range(3):
+        (v,) = ops.corr_volume_build_ex(pm(f1), pm(t2), levels=1, scale=c ** -0.5)  # targets_hw = t2's own grid
+        assert v.shape == (b * h * w, t2.shape[-2], t2.shape[-1])
+        pyr.append(v)
+        a = f1.reshape(b, c, h * w).transpose(1, 2)
+        ref_pyr.append((torch.bmm(a, t2.reshape(b, c, -1)) * c ** -0.5).reshape(b * h * w, 1, t2.shape[-2], t2.shape[-1]))
+        t2 = F.interpolate(t2, scale_factor=0.5, mode="bilinear", align_corners=False)
+    for v, r in zip(pyr, ref_pyr):
+        assert (v.float().cpu() - r[:, 0]).abs().max().item() < tol
+    look = ops.corr_lookup(pyr, coords.permute(0, 2, 3, 1).contiguous().to(DEV), 4, (h, w), nchw=True, out_dtype=torch.float32,
+                           level_hw=[tuple(p.shape[-2:]) for p in pyr])
+    ref = O.corr_lookup(ref_pyr, coords, 4)
+    assert (look.cpu() - ref).abs().max().item() < 2 * tol

@@ -1,9 +1,13 @@
 """GPU parity tests, end to end: ptlflow_b200.get_model(...)(inputs) against vectors produced by the
 reference model (tests/golden/e2e_*.npz) and against the oracle at other shapes.
 
-Gates (BASELINE.json north_star): fp32 <= 1e-3 max-abs on the predicted flow; f16/bf16 are compared
-to the *fp32* reference (the reference's own half path is 0.16-0.28 px away from its fp32 path,
-SURVEY.md section 7) with the measured bound written below.
+Gates (BASELINE.json north_star): fp32 <= 1e-3 max-abs on the predicted flow.  f16/bf16 are compared to the
+*fp32* reference.  north_star's 1e-2 is met by the MEAN-abs error in f16 and missed by the max-abs error by up to
+2.3x (measured 0.009-0.023 px; bf16 0.05-0.16 px); the reference's own half model is 0.16-0.28 px (f16) / 1.7-4.2 px
+(bf16) away from its fp32 output.  tools/f16_error_budget.py attributes > 90 % of the residual to single-pass f16
+operand rounding of the context encoder and the GRU weights (static perturbations seen identically by every
+iteration); halving it needs hi/lo split operands = two tensor-core passes.  The gates are the measured bounds with
+~1.7x margin, not the old 0.25 / 2.0.
 """
 import json
 import os
@@ -75,8 +79,9 @@ def test_half_against_fp32_reference(name, dtype):
     err = np.abs(out["flows_fp32"].cpu().numpy() - g["flows"]).max()
     mean = np.abs(out["flows_fp32"].cpu().numpy() - g["flows"]).mean()
     _report(test="half_vs_fp32_ref", case=name, dtype=str(dtype), err_flow=float(err), mean_err=float(mean), max_flow=float(np.abs(g["flows"]).max()))
-    bound = 0.25 if dtype == torch.float16 else 2.0
+    bound, mean_bound = (4e-2, 1e-2) if dtype == torch.float16 else (3e-1, 6e-2)
     assert err < bound, f"{name} {dtype}: max-abs flow error {err}"
+    assert mean < mean_bound, f"{name} {dtype}: mean-abs flow error {mean}"
 
 
 @pytest.mark.parametrize("variant,iters,b,h,w", [("raft", 3, 1, 436, 1024), ("raft_small", 2, 2, 200, 328)])
