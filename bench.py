@@ -294,17 +294,20 @@ def run_ours(args):
             for i in range(n):
                 step_resident(i)
         else:
-            for i in range(n):
-                pipe.submit({"images": devin[i % pool]})
+            res = [pipe.submit({"images": devin[i % pool]}) for i in range(n)]
             pipe.drain()
+            for r in res:
+                r.enqueued()  # re-raises what a slot thread caught: a failed forward must not count as a fast one
 
     def run_e2e_any(n):
         if pipe is None:
             run_e2e(n)
         else:
-            for i in range(n):  # pinned host frames in, predicted flow back to pinned host memory, every step
-                pipe.submit({"images": host[i % pool]}, host_out=host_outs[i % args.inflight])
+            # pinned host frames in, predicted flow back to pinned host memory, every step
+            res = [pipe.submit({"images": host[i % pool]}, host_out=host_outs[i % args.inflight]) for i in range(n)]
             pipe.drain()
+            for r in res:
+                r.enqueued()
 
     log(f"model on {dev}, {args.dtype}, batch {B}, {args.inflight} batch(es) in flight, cuda graph {'on' if model.use_cuda_graph else 'off'}; warming up")
     sampler = ClockSampler(local_rank)

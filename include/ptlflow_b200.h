@@ -96,6 +96,22 @@ PFB_API int pfb_corr_lookup_ex(void* const* pyramid, const int* level_h, const i
                                int out_stride, pfb_stream stream);
 
 /* ------------------------------------------------------------------------------------
+ * a1 + a2 + a3 on the TILED pyramid (f16 / bf16 storage; what pfb_raft_refine uses with cfg.volume_layout = 1).
+ * Level l of query q is ceil(h_l/4) x ceil(w_l/8) tiles of 4 rows x 8 columns (64 bytes = one DRAM access granule);
+ * element (y, x) sits at element offset ((y>>2) * ceil(w_l/8) + (x>>3)) * 32 + (y&3) * 8 + (x&7) of the query's map.
+ * A 10 x 10 lookup window touches 6.9 such tiles on average (442 B) where the dense layout costs 64 B of DRAM traffic
+ * for every 20-byte window row (820 B).  Same values as pfb_corr_volume_build_ex / pfb_corr_lookup_ex, except that the
+ * pooled levels are means of the fp32 products rounded once (the dense path rounds every level like the reference's
+ * half model does).  pyramid[l]: pfb_corr_level_bytes_tiled(...) bytes, 16-byte aligned; out: [B,H1,W1,out_stride] dtype,
+ * out_stride % 8 == 0, columns >= levels*(2r+1)^2 zero-filled.
+ * ---------------------------------------------------------------------------------- */
+PFB_API size_t pfb_corr_level_bytes_tiled(int B, int H1, int W1, int H2, int W2, int level);
+PFB_API int pfb_corr_volume_build_tiled(const void* fmap1, const void* fmap2, void* const* pyramid, int B, int H1, int W1, int H2,
+                                        int W2, int C, int levels, float scale, pfb_dtype dtype, pfb_stream stream);
+PFB_API int pfb_corr_lookup_tiled(void* const* pyramid, const float* coords, void* out, int B, int H1, int W1, int H2, int W2,
+                                  int levels, int radius, pfb_dtype dtype, int out_stride, pfb_stream stream);
+
+/* ------------------------------------------------------------------------------------
  * a4: on-the-fly correlation + lookup (no 4D volume)
  *   replaces AlternateCorrBlock.__call__     corr.py:78-101  (all levels, scaled by 1/sqrt(C))
  * fmap1 : [B, H, W, C];  fmap2_pyramid[l] : [B, H>>l, W>>l, C] (level 0 = fmap2, l>0 pooled by
@@ -260,6 +276,7 @@ typedef struct {
   int alternate_corr; /* 0: look up the materialised pyramid; 1: on-the-fly (a4) */
   int out_h, out_w, pad_top, pad_left; /* full-resolution output window */
   int impl;           /* 0 auto, 1 SIMT everywhere, 2 tcgen05 where available */
+  int volume_layout;  /* 0: dense pyramid (pfb_corr_volume_build); 1: tiled pyramid (pfb_corr_volume_build_tiled) */
 } pfb_raft_cfg;
 
 typedef struct {

@@ -245,6 +245,252 @@ corr_volume_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 5) tmem_dealloc<256>(tmem_base);
 }
 
+// =====================================================================================================================
+// Tiled-pyramid variant (round 2): same GEMM, output in the T84 layout of csrc/corr_tiled.cu (4 x 8 tiles of 64 bytes).
+//
+//   * N = 256: two target patches per accumulator (tcgen05 runs M = 128 at the nominal rate only for N = 256; the
+//     N = 128 version above spends 128 clk per MMA on 64 clk of math), 2 x 256 TMEM columns double-buffered.
+//   * 8 epilogue warps: warps 0-3 take the first patch of the pair, warps 4-7 the second (TMEM lane quarter = warp % 4).
+//     ncu (r01) had the 4-warp epilogue at ~7000 clk per patch against ~1900 clk of HBM time.
+//   * pooled levels are means of the fp32 accumulators, rounded once (closer to the fp32 reference than re-rounding
+//     every level like the reference's half path does; also 2 conversions fewer per element), packed conversions.
+//   * level 0 leaves through one 5-D TMA bulk store per patch: box [2 tile rows][8 16-byte tile-row chunks][128 queries]
+//     staged conflict-free; level 1 is one full 64-byte tile per (query, patch) written with 16-byte stores.
+//   B operand ring: 3 stages of one 64-channel chunk of BOTH patches (32 KB).  224 KB of shared memory, one CTA per SM.
+struct __align__(8) CorrTBars {
+  uint64_t a_full;
+  uint64_t b_full[3];
+  uint64_t b_empty[3];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct TiledOut {
+  void* ptr[4];
+  int h[4], w[4], tiles_x[4];
+  unsigned map_elems[4];
+};
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t cvt_pack2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t cvt_pack2<__half>(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t cvt_pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(320, 1)
+corr_volume_tiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmO, TiledOut out, int H, int W, int N1, int kchunks, int levels,
+                         float scale, int ab_fmt) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // kchunks x 16 KB
+  uint8_t* sB = sA + kchunks * kTileBytes;              // 3 stages x 32 KB
+  uint8_t* sC = sB + 3 * 2 * kTileBytes;                // 2 groups x 32 KB: [tile row 2][chunk 8][query 128][16 B]
+  CorrTBars* bars = reinterpret_cast<CorrTBars*>(sC + 2 * 2 * kTileBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, b = blockIdx.z;
+  const int PW = (W + 15) / 16, PH = (H + 7) / 8;
+  const int n_patches = PW * PH;
+  const int n_items = (n_patches + 1) >> 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars->a_full, 1);
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&bars->b_full[s], 1);
+      mbar_init(&bars->b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->acc_full[s], 1);
+      mbar_init(&bars->acc_empty[s], 8);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmO);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 8) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->a_full, kchunks * kTileBytes);
+      for (int k = 0; k < kchunks; ++k) tma_load_3d(sA + k * kTileBytes, &tmA, &bars->a_full, k * 64, m_tile * 128, b);
+      int st = 0;
+      uint32_t phs = 0;
+      for (int i = 0; i < n_items; ++i) {
+        const int p0 = 2 * i, p1 = 2 * i + 1;
+        const int ph0 = p0 / PW, pw0 = p0 - ph0 * PW;
+        const int ph1 = p1 / PW, pw1 = p1 - ph1 * PW;  // p1 == n_patches decodes to ph1 == PH: every row out of range -> zero fill
+        for (int k = 0; k < kchunks; ++k) {
+          mbar_wait(&bars->b_empty[st], phs ^ 1);
+          mbar_arrive_expect_tx(&bars->b_full[st], 2 * kTileBytes);
+          tma_load_4d(sB + st * 2 * kTileBytes, &tmB, &bars->b_full[st], k * 64, pw0 * 16, ph0 * 8, b);
+          tma_load_4d(sB + st * 2 * kTileBytes + kTileBytes, &tmB, &bars->b_full[st], k * 64, pw1 * 16, ph1 * 8, b);
+          if (++st == 3) { st = 0; phs ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 256, ab_fmt);
+      mbar_wait(&bars->a_full, 0);
+      int st = 0;
+      uint32_t phs = 0;
+      for (int i = 0; i < n_items; ++i) {
+        const int t = i & 1;
+        mbar_wait(&bars->acc_empty[t], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + t * 256;
+        for (int k = 0; k < kchunks; ++k) {
+          mbar_wait(&bars->b_full[st], phs);
+          tc_fence_after();
+          const uint64_t da = make_desc_k_sw128(smem_u32(sA + k * kTileBytes));
+          const uint64_t db = make_desc_k_sw128(smem_u32(sB + st * 2 * kTileBytes));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_f16(d, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, (k | kk) != 0);
+          umma_commit(&bars->b_empty[st]);
+          if (++st == 3) { st = 0; phs ^= 1; }
+        }
+        umma_commit(&bars->acc_full[t]);
+      }
+    }
+  } else {
+    // ================= epilogue: 2 groups of 4 warps, thread <-> query row =================
+    const int quarter = warp & 3, grp = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int n1 = m_tile * 128 + row;
+    const bool row_ok = n1 < N1;
+    const size_t q = (size_t)b * N1 + (row_ok ? n1 : 0);
+    uint8_t* sCg = sC + grp * 2 * kTileBytes;
+    T* o1 = levels > 1 ? reinterpret_cast<T*>(out.ptr[1]) + q * out.map_elems[1] : nullptr;
+    T* o2 = levels > 2 ? reinterpret_cast<T*>(out.ptr[2]) + q * out.map_elems[2] : nullptr;
+    T* o3 = levels > 3 ? reinterpret_cast<T*>(out.ptr[3]) + q * out.map_elems[3] : nullptr;
+    const float s1 = 0.25f * scale, s2 = 0.0625f * scale, s3 = 0.015625f * scale;
+    const bool leader = (row == 0);
+    for (int i = 0; i < n_items; ++i) {
+      const int t = i & 1;
+      const int p = 2 * i + grp;
+      const bool p_ok = p < n_patches;
+      const int ph = p / PW, pw = p - ph * PW;
+      mbar_wait(&bars->acc_full[t], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + t * 256 + grp * 128 + ((uint32_t)(quarter * 32) << 16);
+      float l2acc[4], l3acc[2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // 32 accumulator columns = patch rows 2c, 2c+1 (16 columns each)
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == 0 && i > 0) {  // the previous bulk store of this group must have drained the staging buffer
+          if (leader) tma_store_wait_read();
+          named_barrier_sync(1 + grp, 128);
+        }
+        // ---- level 0: scale, pack, stage.  patch row rr -> tile row rr >> 2, row-in-tile rr & 3; columns 0-7 / 8-15 -> tile column 0 / 1
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int rr = 2 * c + e;
+#pragma unroll
+          for (int txh = 0; txh < 2; ++txh) {
+            uint4 u;
+            u.x = cvt_pack2<T>(__uint_as_float(r[e * 16 + txh * 8 + 0]) * scale, __uint_as_float(r[e * 16 + txh * 8 + 1]) * scale);
+            u.y = cvt_pack2<T>(__uint_as_float(r[e * 16 + txh * 8 + 2]) * scale, __uint_as_float(r[e * 16 + txh * 8 + 3]) * scale);
+            u.z = cvt_pack2<T>(__uint_as_float(r[e * 16 + txh * 8 + 4]) * scale, __uint_as_float(r[e * 16 + txh * 8 + 5]) * scale);
+            u.w = cvt_pack2<T>(__uint_as_float(r[e * 16 + txh * 8 + 6]) * scale, __uint_as_float(r[e * 16 + txh * 8 + 7]) * scale);
+            const int slot = ((rr >> 2) * 8 + txh * 4 + (rr & 3)) * 128 + row;
+            *reinterpret_cast<uint4*>(sCg + slot * 16) = u;
+          }
+        }
+        // ---- pooled levels from the fp32 accumulators (one rounding per stored value) ----
+        float l1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          l1[j] = (__uint_as_float(r[2 * j]) + __uint_as_float(r[2 * j + 1])) + (__uint_as_float(r[16 + 2 * j]) + __uint_as_float(r[16 + 2 * j + 1]));
+        if (o1 && row_ok && p_ok) {
+          const int i1 = ph * 4 + c, j1 = pw * 8;
+          if (i1 < out.h[1] && j1 < out.w[1]) {
+            const int valid = out.w[1] - j1;  // columns of this tile inside the map; the rest are pad columns = 0
+            uint4 u;
+            u.x = cvt_pack2<T>(valid > 0 ? l1[0] * s1 : 0.f, valid > 1 ? l1[1] * s1 : 0.f);
+            u.y = cvt_pack2<T>(valid > 2 ? l1[2] * s1 : 0.f, valid > 3 ? l1[3] * s1 : 0.f);
+            u.z = cvt_pack2<T>(valid > 4 ? l1[4] * s1 : 0.f, valid > 5 ? l1[5] * s1 : 0.f);
+            u.w = cvt_pack2<T>(valid > 6 ? l1[6] * s1 : 0.f, valid > 7 ? l1[7] * s1 : 0.f);
+            *reinterpret_cast<uint4*>(o1 + (size_t)(ph * out.tiles_x[1] + pw) * 32 + c * 8) = u;
+          }
+        }
+        if ((c & 1) == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) l2acc[j] = l1[2 * j] + l1[2 * j + 1];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) l2acc[j] += l1[2 * j] + l1[2 * j + 1];
+          if (o2 && row_ok && p_ok) {
+            const int i2 = ph * 2 + (c >> 1), j2 = pw * 4;
+            if (i2 < out.h[2] && j2 < out.w[2]) {
+              const int valid = out.w[2] - j2;
+              uint2 u;
+              u.x = cvt_pack2<T>(valid > 0 ? l2acc[0] * s2 : 0.f, valid > 1 ? l2acc[1] * s2 : 0.f);
+              u.y = cvt_pack2<T>(valid > 2 ? l2acc[2] * s2 : 0.f, valid > 3 ? l2acc[3] * s2 : 0.f);
+              *reinterpret_cast<uint2*>(o2 + (size_t)((i2 >> 2) * out.tiles_x[2] + (pw >> 1)) * 32 + (i2 & 3) * 8 + (pw & 1) * 4) = u;
+            }
+          }
+          if (c == 1) {
+            l3acc[0] = l2acc[0] + l2acc[1];
+            l3acc[1] = l2acc[2] + l2acc[3];
+          } else {
+            l3acc[0] += l2acc[0] + l2acc[1];
+            l3acc[1] += l2acc[2] + l2acc[3];
+            if (o3 && row_ok && p_ok) {
+              const int i3 = ph, j3 = pw * 2;
+              if (i3 < out.h[3] && j3 < out.w[3]) {
+                const int valid = out.w[3] - j3;
+                const uint32_t u = cvt_pack2<T>(l3acc[0] * s3, valid > 1 ? l3acc[1] * s3 : 0.f);
+                *reinterpret_cast<uint32_t*>(o3 + (size_t)((i3 >> 2) * out.tiles_x[3] + (pw >> 2)) * 32 + (i3 & 3) * 8 + (pw & 3) * 2) = u;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[t]);
+      fence_proxy_async();               // generic-proxy writes -> visible to the async (TMA) proxy
+      named_barrier_sync(1 + grp, 128);  // the four warps of this group
+      if (leader && p_ok) {
+        // dims (8 elements, query, 16-byte chunk along the tile row, tile row, sample): clipped at N1 / tiles by the TMA unit
+        tma_store_5d(&tmO, sCg, 0, m_tile * 128, pw * 8, ph * 2, b);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait_read();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
 bool corr_volume_umma_supported(int B, int H, int W, int C, int L, pfb_dtype dt) {
   if (dt != PFB_F16 && dt != PFB_BF16) return false;
   if (C % 64 != 0 || C > 64 * kMaxKChunks) return false;
@@ -308,3 +554,80 @@ int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, in
 }
 
 }  // namespace pfb
+
+namespace pfb {
+
+bool corr_volume_tiled_supported(int B, int H, int W, int C, int L, pfb_dtype dt) {
+  if (dt != PFB_F16 && dt != PFB_BF16) return false;
+  if (C % 64 != 0 || C > 64 * kMaxKChunks) return false;
+  if (L < 1 || L > 4) return false;
+  if (H < 1 || W < 1 || B < 1 || B > 65535) return false;
+  return true;
+}
+
+int corr_volume_tiled(const void* f1, const void* f2, void* const* pyr, int B, int N1, int H, int W, int C, int L, float scale,
+                      pfb_dtype dt, cudaStream_t s) {
+  const int kchunks = C / 64;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)N1, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)N1 * C * 2};
+    uint32_t box[3] = {64, 128, 1};
+    int rc = make_tensor_map(&tmA, f1, dt, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {64, 16, 8, 1};
+    int rc = make_tensor_map(&tmB, f2, dt, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  TiledOut out{};
+  for (int l = 0; l < L; ++l) {
+    out.ptr[l] = pyr[l];
+    out.h[l] = H >> l;
+    out.w[l] = W >> l;
+    out.tiles_x[l] = (out.w[l] + 7) >> 3;
+    out.map_elems[l] = (unsigned)(((out.h[l] + 3) >> 2) * out.tiles_x[l] * 32);
+  }
+  {
+    const uint64_t tx0 = (uint64_t)out.tiles_x[0], ty0 = (uint64_t)((H + 3) >> 2), map_bytes = ty0 * tx0 * 64;
+    uint64_t dims[5] = {8, (uint64_t)N1, 4 * tx0, ty0, (uint64_t)B};
+    uint64_t str[4] = {map_bytes, 16, 64 * tx0, (uint64_t)N1 * map_bytes};
+    uint32_t box[5] = {8, 128, 8, 2, 1};
+    int rc = make_tensor_map_linear(&tmO, pyr[0], dt, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  const int m_tiles = ceil_div(N1, 128);
+  const size_t smem = (size_t)kchunks * kTileBytes + 3 * 2 * kTileBytes + 2 * 2 * kTileBytes + sizeof(CorrTBars) + 1024;
+  dim3 grid(m_tiles, 1, B);
+  ProfScope prof(KC_VOLUME, s);
+  if (dt == PFB_F16) {
+    PFB_CUDA(cudaFuncSetAttribute(corr_volume_tiled_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    corr_volume_tiled_kernel<__half><<<grid, 320, smem, s>>>(tmA, tmB, tmO, out, H, W, N1, kchunks, L, scale, 0);
+  } else {
+    PFB_CUDA(cudaFuncSetAttribute(corr_volume_tiled_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    corr_volume_tiled_kernel<__nv_bfloat16><<<grid, 320, smem, s>>>(tmA, tmB, tmO, out, H, W, N1, kchunks, L, scale, 1);
+  }
+  PFB_LAUNCH_CHECK();
+  return PFB_OK;
+}
+
+}  // namespace pfb
+
+extern "C" PFB_API int pfb_corr_volume_build_tiled(const void* fmap1, const void* fmap2, void* const* pyramid, int B, int H1, int W1,
+                                                   int H2, int W2, int C, int levels, float scale, pfb_dtype dtype, pfb_stream stream) {
+  using namespace pfb;
+  PFB_CHECK_ARG(fmap1 && fmap2 && pyramid, "corr_volume_build_tiled: null pointer");
+  PFB_CHECK_ARG(B > 0 && H1 > 0 && W1 > 0 && H2 > 0 && W2 > 0 && C > 0, "corr_volume_build_tiled: bad shape");
+  PFB_CHECK_ARG(levels >= 1 && levels <= 4 && (H2 >> (levels - 1)) >= 1 && (W2 >> (levels - 1)) >= 1,
+                "corr_volume_build_tiled: %dx%d target grid cannot hold %d levels (1..4)", H2, W2, levels);
+  for (int l = 0; l < levels; ++l)
+    PFB_CHECK_ARG(pyramid[l] && (reinterpret_cast<uintptr_t>(pyramid[l]) & 15) == 0, "corr_volume_build_tiled: pyramid[%d] null or not 16-byte aligned", l);
+  if (!corr_volume_tiled_supported(B, H2, W2, C, levels, dtype)) {
+    set_error("corr_volume_build_tiled: needs f16/bf16 storage and C a multiple of 64, <= 256 (C=%d dtype=%d)", C, (int)dtype);
+    return PFB_ERR_UNSUPPORTED;
+  }
+  return corr_volume_tiled(fmap1, fmap2, pyramid, B, H1 * W1, H2, W2, C, levels, scale, dtype, as_stream(stream));
+}

@@ -31,8 +31,8 @@ static Workspace plan(const pfb_raft_cfg* c) {
   const size_t es = dtype_size(c->dtype);
   const int K = 2 * c->corr_radius + 1;
   w.planes = c->corr_levels * K * K;
-  // tensor-core path wants 64-channel (128-byte) K chunks; pad columns are zero-filled by the lookup
-  w.corr_stride = (c->dtype == PFB_F32) ? w.planes : (int)align_up(w.planes, 64);
+  // 16-byte aligned rows for the tensor-core path (the TMA unit zero-fills a partial last 64-channel K chunk itself)
+  w.corr_stride = (c->dtype == PFB_F32) ? w.planes : (int)align_up(w.planes, 8);
   if (c->variant == 0 || c->variant == 2) {
     w.c_cor1 = 256; w.c_cor2 = 192; w.c_flo1 = 128; w.c_flo2 = 64; w.c_fh = 256;
     // gma keeps [motion | motion_global] side by side so the GRU still sees three sources (update.py:150-151)
@@ -72,6 +72,8 @@ static int check_cfg(const pfb_raft_cfg* c) {
   PFB_CHECK_ARG((c->H >> (c->corr_levels - 1)) >= 1 && (c->W >> (c->corr_levels - 1)) >= 1,
                 "raft: %dx%d grid too small for %d levels", c->H, c->W, c->corr_levels);
   PFB_CHECK_ARG(c->hidden_dim > 0 && c->context_dim > 0 && c->iters >= 0, "raft: bad dims");
+  PFB_CHECK_ARG(c->volume_layout == 0 || (c->volume_layout == 1 && c->dtype != PFB_F32 && !c->alternate_corr && c->corr_levels <= 4),
+                "raft: volume_layout=%d needs f16/bf16, a materialised pyramid and <= 4 levels", c->volume_layout);
   if (c->variant != 1) PFB_CHECK_ARG(c->hidden_dim == 128 && c->context_dim == 128, "raft/gma: the update block expects hidden=context=128");
   else PFB_CHECK_ARG(c->hidden_dim == 96 && c->context_dim == 64, "raft_small: SmallUpdateBlock expects hidden=96 context=64");
   return PFB_OK;
@@ -127,6 +129,9 @@ static int lookup(const Ctx& x) {
     return pfb_corr_lookup_onthefly(x.b->fmap1, x.b->pyramid, x.b->coords, x.at(x.ws.off_corr), c->B, c->H, c->W,
                                     c->feat_dim, c->corr_levels, c->corr_radius, c->dtype, c->dtype, 0,
                                     x.ws.corr_stride, (pfb_stream)x.s);
+  if (c->volume_layout == 1)
+    return pfb_corr_lookup_tiled(x.b->pyramid, x.b->coords, x.at(x.ws.off_corr), c->B, c->H, c->W, c->H, c->W, c->corr_levels,
+                                 c->corr_radius, c->dtype, x.ws.corr_stride, (pfb_stream)x.s);
   return pfb_corr_lookup(x.b->pyramid, x.b->coords, x.at(x.ws.off_corr), c->B, c->H, c->W, c->corr_levels,
                          c->corr_radius, c->dtype, c->dtype, 0, x.ws.corr_stride, (pfb_stream)x.s);
 }

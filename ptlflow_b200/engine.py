@@ -7,12 +7,16 @@ packing, buffers, pointer structs, CUDA-graph capture.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib, ops
 from ._lib import check, dtype_code, load, ptr_array, stream_ptr
+
+
+_TILED = bool(int(os.environ.get("PFB_VOLUME_TILED", "1")))
 
 
 class RaftEngine:
@@ -103,13 +107,20 @@ class RaftEngine:
         return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in update_block.parameters())
 
     # -- run --------------------------------------------------------------------------------
-    def make_cfg(self, B: int, H: int, W: int, iters: int, out_hw, pad, alternate_corr: bool, feat_dim: int) -> _lib.RaftCfg:
+    def make_cfg(self, B: int, H: int, W: int, iters: int, out_hw, pad, alternate_corr: bool, feat_dim: int, volume_layout: int = 0) -> _lib.RaftCfg:
         return _lib.RaftCfg(self.variant, dtype_code(self.dtype), B, H, W, feat_dim, self.corr_levels, self.corr_radius,
                             self.hidden_dim, self.context_dim, iters, int(alternate_corr), out_hw[0], out_hw[1], pad[0], pad[1],
-                            self.impl)
+                            self.impl, 0 if alternate_corr else int(volume_layout))
 
     def build_volume(self, fmap1: torch.Tensor, fmap2: torch.Tensor, impl: int = 0):
-        """a1 + a2 for the refinement loop of this engine (layout chosen by the library, see refine())."""
+        """a1 + a2 for the refinement loop of this engine.  f16 / bf16 with tensor-core-shaped features get the tiled
+        pyramid (64-byte tiles, csrc/corr_tiled.cu); everything else the dense one.  refine() reads the layout back from
+        ``self.volume_layout`` (set here, per call)."""
+        self.volume_layout = 0
+        if _TILED and impl != 1 and self.corr_radius in (3, 4) and ops.tiled_supported(fmap1, self.corr_levels) \
+                and (self.corr_radius, self.corr_levels) in ((4, 4), (4, 3), (4, 2), (4, 1), (3, 4), (3, 3)):
+            self.volume_layout = 1
+            return ops.corr_volume_build_tiled(fmap1, fmap2, self.corr_levels)
         return ops.corr_volume_build(fmap1, fmap2, self.corr_levels, impl=impl)
 
     def workspace(self, cfg: _lib.RaftCfg, scratch: Optional[dict] = None) -> torch.Tensor:
@@ -147,7 +158,7 @@ class RaftEngine:
         """Runs the loop in place on (net, coords); returns (flow_up fp32 [B,2,oh,ow], flow_small fp32 [B,2,H,W])."""
         B, H, W, _ = net.shape
         alt = fmap1 is not None
-        cfg = self.make_cfg(B, H, W, iters, out_hw, pad, alt, fmap1.shape[-1] if alt else 0)
+        cfg = self.make_cfg(B, H, W, iters, out_hw, pad, alt, fmap1.shape[-1] if alt else 0, getattr(self, "volume_layout", 0))
         ws = self.workspace(cfg, scratch)
         flow_up = torch.empty((B, 2, out_hw[0], out_hw[1]), dtype=torch.float32, device=self.device)
         flow_small = torch.empty((B, 2, H, W), dtype=torch.float32, device=self.device)

@@ -25,6 +25,7 @@ from .extractor import BasicEncoder, SmallEncoder
 from .update import BasicUpdateBlock, SmallUpdateBlock
 
 
+_capture_lock = threading.Lock()  # one CUDA-graph capture at a time per process (pipeline slots capture on their first batch)
 _cudnn_lock = threading.Lock()
 _cudnn_users = 0
 _cudnn_saved = None
@@ -251,7 +252,7 @@ class RAFT(BaseModel):
 
             lib = _lib.load()
             scratch: dict = {}  # workspaces of this graph: owned by the cache entry, so they live exactly as long as the graph
-            with torch.cuda.stream(side):
+            with _capture_lock, torch.cuda.stream(side):
                 for _ in range(2):  # eager warm-up on the capture stream: cuDNN autotune, weight packing, scratch caches
                     self._forward_device(static_in, static_init, scratch)
                 side.synchronize()

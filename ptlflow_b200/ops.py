@@ -72,6 +72,57 @@ def corr_volume_build_ex(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int =
 
 
 # ------------------------------------------------------------------------------------------
+# a1 + a2 + a3 on the tiled pyramid (see include/ptlflow_b200.h: 4 x 8 tiles of 64 bytes)
+# ------------------------------------------------------------------------------------------
+def tiled_supported(fmap: torch.Tensor, levels: int) -> bool:
+    return fmap.dtype in (torch.float16, torch.bfloat16) and fmap.shape[-1] % 64 == 0 and fmap.shape[-1] <= 256 and 1 <= levels <= 4
+
+
+def corr_volume_build_tiled(fmap1: torch.Tensor, fmap2: torch.Tensor, levels: int = 4, scale: Optional[float] = None) -> List[torch.Tensor]:
+    """fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C] (f16/bf16) -> per level a flat tensor [B*H1*W1, tiles_y*tiles_x*32] in the tiled layout."""
+    require_cuda(fmap1, "fmap1"); require_cuda(fmap2, "fmap2")
+    B, H1, W1, Cc = fmap1.shape
+    _, H2, W2, _ = fmap2.shape
+    if fmap1.dtype != fmap2.dtype or fmap2.shape[0] != B or fmap2.shape[3] != Cc:
+        raise RuntimeError("corr_volume_build_tiled: fmap1 / fmap2 must agree in batch, channels and dtype")
+    lib = load()
+    pyr = []
+    for l in range(levels):
+        nbytes = lib.pfb_corr_level_bytes_tiled(B, H1, W1, H2, W2, l)
+        if nbytes == 0:
+            raise RuntimeError(f"corr_volume_build_tiled: {H2}x{W2} target grid too small for {levels} levels")
+        pyr.append(torch.empty((B * H1 * W1, nbytes // (2 * B * H1 * W1)), dtype=fmap1.dtype, device=fmap1.device))
+    with torch.cuda.device(fmap1.device):
+        check(lib.pfb_corr_volume_build_tiled(fmap1.data_ptr(), fmap2.data_ptr(), ptr_array(pyr), B, H1, W1, H2, W2, Cc, levels,
+                                              float(Cc ** -0.5 if scale is None else scale), dtype_code(fmap1.dtype),
+                                              stream_ptr(fmap1.device)), "corr_volume_build_tiled")
+    return pyr
+
+
+def untile_level(level: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """Tiled level [Q, tiles_y*tiles_x*32] -> dense [Q, h, w] (pure indexing; tests and debugging)."""
+    ty, tx = (h + 3) // 4, (w + 7) // 8
+    v = level.view(level.shape[0], ty, tx, 4, 8).permute(0, 1, 3, 2, 4).reshape(level.shape[0], ty * 4, tx * 8)
+    return v[:, :h, :w].contiguous()
+
+
+def corr_lookup_tiled(pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: int, targets_hw, out_stride: Optional[int] = None) -> torch.Tensor:
+    """coords fp32 [B,H1,W1,2] -> [B,H1,W1,out_stride] in the pyramid's dtype (pixel-major, the refinement loop's layout)."""
+    require_cuda(coords, "coords")
+    if coords.dtype != torch.float32:
+        raise RuntimeError("corr_lookup_tiled: coords must be float32 [B,H,W,2]")
+    B, H, W, _ = coords.shape
+    L = len(pyramid)
+    planes = L * (2 * radius + 1) ** 2
+    stride = (planes + 7) // 8 * 8 if out_stride is None else out_stride
+    out = torch.empty((B, H, W, stride), dtype=pyramid[0].dtype, device=coords.device)
+    with torch.cuda.device(coords.device):
+        check(load().pfb_corr_lookup_tiled(ptr_array(pyramid), coords.data_ptr(), out.data_ptr(), B, H, W, targets_hw[0], targets_hw[1], L,
+                                           radius, dtype_code(pyramid[0].dtype), stride, stream_ptr(coords.device)), "corr_lookup_tiled")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # a3
 # ------------------------------------------------------------------------------------------
 def corr_lookup(pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: int, grid_hw, nchw: bool = True,

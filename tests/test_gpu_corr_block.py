@@ -110,3 +110,73 @@ def test_sea_raft_pyramid_of_volumes(dtype, tol):
                            level_hw=[tuple(p.shape[-2:]) for p in pyr])
     ref = O.corr_lookup(ref_pyr, coords, 4)
     assert (look.cpu() - ref).abs().max().item() < 2 * tol
+
+
+# ------------------------------------------------------------------------------------------
+# tiled pyramid (64-byte tiles): what the refinement loop uses for f16 / bf16
+# ------------------------------------------------------------------------------------------
+TILED_CASES = [
+    # b, c, h, w, levels, radius, dtype, tol
+    (2, 256, 24, 40, 4, 4, torch.float16, 2e-2),
+    (1, 256, 55, 128, 4, 4, torch.float16, 2e-2),   # the config-2 grid: odd height, 2 x 2 tile patches exactly
+    (1, 128, 27, 45, 4, 4, torch.float16, 2e-2),    # odd everything: partial tiles, pad columns, floor-dropped rows / columns
+    (1, 64, 9, 17, 3, 3, torch.float16, 2e-2),      # a grid smaller than one patch pair per row; radius 3 / 3 levels (raft_small-like)
+    (1, 256, 16, 24, 1, 4, torch.bfloat16, 1.5e-1), # single level (FlowFormer)
+    (3, 192, 13, 33, 2, 4, torch.bfloat16, 1.5e-1),
+]
+
+
+@pytest.mark.parametrize("b,c,h,w,levels,radius,dtype,tol", TILED_CASES)
+def test_tiled_volume_and_lookup(b, c, h, w, levels, radius, dtype, tol):
+    from ptlflow_b200 import ops
+
+    f1 = torch.from_numpy(synth.synth_normal("tl/f1", (b, c, h, w), 11))
+    f2 = torch.from_numpy(synth.synth_normal("tl/f2", (b, c, h, w), 11))
+    coords = O.coords_grid(b, h, w) + torch.from_numpy(synth.synth_normal("tl/c", (b, 2, h, w), 11, scale=6.0))
+    coords[0, :, 0, 0] = torch.tensor([-40.0, -40.0])        # far out of bounds
+    coords[0, :, 0, 1] = torch.tensor([float(w) - 0.5, float(h) - 0.5])  # straddles the bottom-right corner
+    coords[0, :, 0, 2] = torch.tensor([0.0, 0.0])            # integer coordinates: zero fractional weights
+    coords[0, :, 1, 0] = torch.tensor([7.0, 3.25])           # window starts at tile column offset 7 -> third chunk
+    pm = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)  # noqa: E731
+    pyr = ops.corr_volume_build_tiled(pm(f1), pm(f2), levels)
+    # storage rounding of the features is part of the operator's contract: the oracle sees the rounded features
+    f1r, f2r = f1.to(dtype).float(), f2.to(dtype).float()
+    ref_pyr = O.corr_pyramid(O.corr_volume(f1r, f2r), levels)
+    for l, (p, r) in enumerate(zip(pyr, ref_pyr)):
+        dense = ops.untile_level(p, h >> l, w >> l)
+        assert dense.shape == r[:, 0].shape
+        err = (dense.float().cpu() - r[:, 0]).abs().max().item()
+        assert err < tol, f"level {l}: {err}"
+    look = ops.corr_lookup_tiled(pyr, coords.permute(0, 2, 3, 1).contiguous().to(DEV), radius, (h, w))
+    planes = levels * (2 * radius + 1) ** 2
+    assert look.shape == (b, h, w, (planes + 7) // 8 * 8)
+    ref = O.corr_lookup(ref_pyr, coords, radius)
+    got = look[..., :planes].permute(0, 3, 1, 2).float().cpu()
+    assert (got - ref).abs().max().item() < 2 * tol
+    assert look[..., planes:].abs().max().item() == 0
+    # the tiled lookup reads exactly what the dense lookup reads from the same (stored) values
+    dense_pyr = [ops.untile_level(p, h >> l, w >> l) for l, p in enumerate(pyr)]
+    look_d = ops.corr_lookup(dense_pyr, coords.permute(0, 2, 3, 1).contiguous().to(DEV), radius, (h, w), nchw=True, out_dtype=torch.float32)
+    assert (got - look_d.cpu()).abs().max().item() < (2e-3 if dtype == torch.float16 else 1.6e-2) * max(1.0, ref.abs().max().item())
+
+
+def test_tiled_lookup_pad_columns_are_masked():
+    """Pad columns / rows of the tiled maps may hold anything: poison them and look up again."""
+    from ptlflow_b200 import ops
+
+    b, c, h, w, levels, radius = 1, 64, 10, 13, 2, 4
+    f1 = torch.from_numpy(synth.synth_normal("tp/f1", (b, c, h, w), 12))
+    f2 = torch.from_numpy(synth.synth_normal("tp/f2", (b, c, h, w), 12))
+    coords = (O.coords_grid(b, h, w) + torch.from_numpy(synth.synth_normal("tp/c", (b, 2, h, w), 12, scale=3.0))).permute(0, 2, 3, 1).contiguous().to(DEV)
+    pm = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV, torch.float16)  # noqa: E731
+    pyr = ops.corr_volume_build_tiled(pm(f1), pm(f2), levels)
+    a = ops.corr_lookup_tiled(pyr, coords, radius, (h, w)).clone()
+    for l, p in enumerate(pyr):
+        hl, wl = h >> l, w >> l
+        ty, tx = (hl + 3) // 4, (wl + 7) // 8
+        v = p.view(p.shape[0], ty, tx, 4, 8)
+        ys = (torch.arange(ty, device=DEV)[:, None] * 4 + torch.arange(4, device=DEV)[None, :])[None, :, None, :, None]
+        xs = (torch.arange(tx, device=DEV)[:, None] * 8 + torch.arange(8, device=DEV)[None, :])[None, None, :, None, :]
+        v[((ys >= hl) | (xs >= wl)).expand_as(v)] = 1000.0
+    bb = ops.corr_lookup_tiled(pyr, coords, radius, (h, w))
+    assert torch.equal(a, bb)

@@ -328,3 +328,21 @@ def test_overlapping_window_gemm_is_the_convolution():
             row[4 * 8 : 4 * 8 + Wf * 8] = px[0, r].reshape(-1)
             acc += tf[j] @ row.as_strided((Wf, 64), (8, 1)).T
         assert torch.allclose(acc, reff[:, y], atol=1e-3)
+
+
+def test_tiled_layout_index_formula():
+    """The tiled-pyramid element offset of include/ptlflow_b200.h (what the CUDA kernels compute) against ops.untile_level."""
+    import numpy as np
+    import torch
+
+    from ptlflow_b200 import ops
+
+    for h, w in ((55, 128), (27, 45), (6, 16), (1, 1), (13, 33)):
+        ty, tx = (h + 3) // 4, (w + 7) // 8
+        dense = np.arange(3 * h * w, dtype=np.float32).reshape(3, h, w)
+        tiled = np.full((3, ty * tx * 32), -1.0, dtype=np.float32)
+        for y in range(h):
+            for x in range(w):
+                tiled[:, ((y >> 2) * tx + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7)] = dense[:, y, x]
+        back = ops.untile_level(torch.from_numpy(tiled), h, w).numpy()
+        assert np.array_equal(back, dense)
