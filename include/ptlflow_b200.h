@@ -187,6 +187,15 @@ typedef struct {
    * by pfb_pack_conv_weight_kmajor: [KH*KW][Cout_pad_k][Cin_pad], every source padded to 64 channels */
   const void* weight_k;
   int Cin_pad, Cout_pad_k;
+  /* optional per-pixel pre-activation term [B,H,W,addend_stride] dtype, added to the accumulator INSTEAD of `bias` before the
+   * epilogue function (the iteration-invariant context part of the GRU gates: conv(inp) + bias, computed once per forward,
+   * update.py:60-63 split by linearity).  addend_stride >= Cout_pad_k, % 8 == 0.  NULL = use bias. */
+  const void* addend;
+  int addend_stride;
+  /* > 0 (1x1 layers, tcgen05 path): sample b multiplies with ITS OWN weight matrix, rows [b * w_rows_per_sample, + Cout_pad_k)
+   * of weight_k [B * w_rows_per_sample][Cin_pad] -- one launch for all samples of "attention @ v" (gma_utils.py:101-113),
+   * where the "weights" are the sample's transposed v.  0 = one weight matrix for all samples. */
+  int w_rows_per_sample;
 } pfb_conv_params;
 
 PFB_API int pfb_conv2d(const pfb_conv_params* p, pfb_stream stream);
@@ -252,6 +261,14 @@ typedef enum {
   PFB_L_FLOW1, PFB_L_FLOW2, PFB_L_MASK1, PFB_L_MASK2,
   PFB_L_AGG_V, /* GMA Aggregate.to_v (1x1, no bias) */
   PFB_L_FLOW2T, /* flow_head.conv2 re-expressed as a 1x1 layer with 18 = 9 taps x 2 outputs (row = tap*2+o) */
+  /* round 2 (tensor-core path only; present iff weight_k != NULL, else the loop uses the layers above):
+   * the context (`inp`) columns of the four GRU convolutions as their own layers, evaluated ONCE per forward ... */
+  PFB_L_CTX_ZR1, PFB_L_CTX_Q1, PFB_L_CTX_ZR2, PFB_L_CTX_Q2,
+  /* ... the same four without those columns (sources: hidden state | motion features), evaluated every iteration ... */
+  PFB_L_GRUX_ZR1, PFB_L_GRUX_Q1, PFB_L_GRUX_ZR2, PFB_L_GRUX_Q2,
+  /* ... and convc2 (256 -> 192) | convf2 (128 -> 64) as ONE block-diagonal 3x3 layer 384 -> 256 (update.py:98-102): N = 256
+   * runs the tensor core at its nominal rate, the two separate layers (N = 192, 64) do not */
+  PFB_L_CONVC2F2,
   PFB_L_COUNT
 } pfb_layer_id;
 

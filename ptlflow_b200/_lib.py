@@ -24,7 +24,8 @@ _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 EPI_LINEAR, EPI_RELU, EPI_GRU_ZR, EPI_GRU_Q, EPI_FLOW, EPI_RELU_APPEND_FLOW, EPI_AXPY, EPI_LINEAR_F32 = range(8)
 
 (L_CONVC1, L_CONVC2, L_CONVF1, L_CONVF2, L_CONV, L_GRU_ZR1, L_GRU_Q1, L_GRU_ZR2, L_GRU_Q2,
- L_FLOW1, L_FLOW2, L_MASK1, L_MASK2, L_AGG_V, L_FLOW2T, L_COUNT) = range(16)
+ L_FLOW1, L_FLOW2, L_MASK1, L_MASK2, L_AGG_V, L_FLOW2T,
+ L_CTX_ZR1, L_CTX_Q1, L_CTX_ZR2, L_CTX_Q2, L_GRUX_ZR1, L_GRUX_Q1, L_GRUX_ZR2, L_GRUX_Q2, L_CONVC2F2, L_COUNT) = range(25)
 
 
 class ConvSrc(C.Structure):
@@ -43,6 +44,7 @@ class ConvParams(C.Structure):
         ("coords", C.c_void_p), ("flow", C.c_void_p),
         ("dtype", C.c_int), ("impl", C.c_int),
         ("weight_k", C.c_void_p), ("Cin_pad", C.c_int), ("Cout_pad_k", C.c_int),
+        ("addend", C.c_void_p), ("addend_stride", C.c_int), ("w_rows_per_sample", C.c_int),
     ]
 
 

@@ -243,5 +243,9 @@ extern "C" PFB_API int pfb_conv2d(const pfb_conv_params* p, pfb_stream stream) {
       return PFB_ERR_UNSUPPORTED;
     }
   }
+  if (p->addend || p->w_rows_per_sample) {
+    set_error("conv2d: per-pixel addend / per-sample weights are implemented by the tcgen05 path only (shape / dtype / impl not eligible)");
+    return PFB_ERR_UNSUPPORTED;
+  }
   return conv2d_simt(p, s);
 }

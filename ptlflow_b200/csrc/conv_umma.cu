@@ -74,6 +74,9 @@ struct ConvUmmaArgs {
   void* aux_z;
   int hidden;
   const float* flow;
+  int w_rows_per_sample;         // > 0: every sample b has its own weight matrix, rows [b * w_rows_per_sample, ...) of the weight map
+  const void* addend;            // optional per-pixel pre-activation term [B*H*W][addend_stride] (storage type), added instead of the bias
+  int addend_stride;
   int ab_fmt;
   unsigned long long* trace;     // debug timeline (PFB_CONV_TRACE): 32 clock64 slots per CTA, null in production
 };
@@ -226,10 +229,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         int n0, b, y0, x0;
         decode(w, n0, b, y0, x0);
         int kidx = 0;
+        const int wrow0 = (b < a.B ? b : 0) * a.w_rows_per_sample;  // per-sample weights (GMA aggregate: the sample's v^T)
         for (int s = 0; s < a.nsrc; ++s) {
           const CUtensorMap* tm = s == 0 ? &tm0 : (s == 1 ? &tm1 : &tm2);
           for (int c = 0; c < a.src_chunks[s]; ++c, ++kidx) {
-            int wrow = 0;  // (ky * KW + kx) * Cout_pad_k
+            int wrow = wrow0;  // + (ky * KW + kx) * Cout_pad_k
             for (int ky = 0; ky < a.KH; ++ky) {
               for (int kx = 0; kx < a.KW; ++kx) {
                 // activation patch: once per (chunk, ky) with the x halo, once per chunk with the y halo, else per tap
@@ -375,10 +379,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           for (int q = 0; q < 4; ++q) zq[q] = reinterpret_cast<const uint4*>(zp)[q];
         }
       };
-      uint4 hnext[4], znext[4];
+      // per-pixel addend (the iteration-invariant context part of the GRU gates, computed once per forward and carrying the
+      // bias): requested one chunk ahead like h / z
+      const T* addp = a.addend ? reinterpret_cast<const T*>(a.addend) + p * a.addend_stride + n0 : nullptr;
+      auto issue_add = [&](int c, uint4 (&aq)[4]) {
+        if (ok && addp) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) hnext[q] = znext[q] = make_uint4(0u, 0u, 0u, 0u);
+          for (int q = 0; q < 4; ++q) aq[q] = reinterpret_cast<const uint4*>(addp + c)[q];
+        }
+      };
+      uint4 hnext[4], znext[4], anext[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hnext[q] = znext[q] = anext[q] = make_uint4(0u, 0u, 0u, 0u);
       if (aux_h_any) issue_aux(group * 32, hnext, znext);
+      issue_add(group * 32, anext);
       mbar_wait(&bars->acc_full[t], tuse & 1);
       tc_fence_after();
       if (warp == 0 && i < 3) PFB_TR(12 + i);
@@ -389,24 +403,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       if (group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
       for (int c = group * 32; c < a.NT; c += 64) {
         const int n = n0 + c;  // first output channel of this chunk
-        float4 bb[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bb[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[32];
         uint4 hraw[4], zraw[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) { hraw[q] = hnext[q]; zraw[q] = znext[q]; }
-        tmem_ld_wait();
-        float v[32];
+        if (addp) {  // warp-uniform: per-pixel addend instead of the per-channel bias
+          uint4 araw[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bb[q].x;
-          v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb[q].y;
-          v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb[q].z;
-          v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb[q].w;
+          for (int q = 0; q < 4; ++q) araw[q] = anext[q];
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8<T>(araw[q], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 * q + e] = __uint_as_float(r[8 * q + e]) + f[e];
+          }
+        } else {
+          float4 bb[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bb[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bb[q].x;
+            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb[q].y;
+            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb[q].z;
+            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb[q].w;
+          }
         }
         if (c + 64 < a.NT) {  // warp-uniform
           tmem_ld_32x32(taddr + c + 64, r);
           if (aux_h_any) issue_aux(c + 64, hnext, znext);
+          issue_add(c + 64, anext);
         }
         if (!ok) continue;
         T* out = reinterpret_cast<T*>(a.out);
@@ -554,6 +583,8 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
     default: return false;
   }
   if (p->out_stride % 8 || p->out_offset % 8) return false;
+  if (p->w_rows_per_sample && (p->KH != 1 || p->KW != 1 || p->w_rows_per_sample < p->Cout_pad_k)) return false;
+  if (p->addend && (p->addend_stride % 8 || (reinterpret_cast<uintptr_t>(p->addend) & 15) || p->addend_stride < p->Cout_pad_k)) return false;
   // N tiling: equal tiles of <= 256 columns, multiple of 32 (epilogue chunk) unless a single small tile
   int n_tiles = ceil_div(p->Cout_pad_k, 256);
   if (p->Cout_pad_k % n_tiles) return false;
@@ -644,11 +675,12 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.n_tiles = ceil_div(p->Cout_pad_k, 256);
   a.NT = p->Cout_pad_k / a.n_tiles;
   // CTA pairs split the weight tile in two: needs an even row count per half (UMMA N % 16) -> NT % 32, always true here
-  const int CG = (env_cg && (sm_count() % 2) == 0) ? 2 : 1;
+  // (per-sample weights: a CTA pair shares one weight tile, and adjacent M tiles may belong to different samples -> single CTAs)
+  const int CG = (env_cg && (sm_count() % 2) == 0 && p->w_rows_per_sample == 0) ? 2 : 1;
   a.acc_stride = a.NT > 128 ? 256 : 128;
   CUtensorMap tmW;
   {
-    uint64_t dims[2] = {(uint64_t)p->Cin_pad, (uint64_t)p->KH * p->KW * p->Cout_pad_k};
+    uint64_t dims[2] = {(uint64_t)p->Cin_pad, p->w_rows_per_sample > 0 ? (uint64_t)p->B * p->w_rows_per_sample : (uint64_t)p->KH * p->KW * p->Cout_pad_k};
     uint64_t str[1] = {(uint64_t)p->Cin_pad * 2};
     uint32_t box[2] = {64, (uint32_t)(a.NT / CG)};
     int rc = make_tensor_map(&tmW, p->weight_k, p->dtype, 2, dims, str, box);
@@ -690,6 +722,8 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.bias = p->bias; a.epilogue = p->epilogue; a.scale = p->scale;
   a.out = p->out; a.out_stride = p->out_stride; a.out_offset = p->out_offset;
   a.aux_h = p->aux_h; a.aux_z = p->aux_z; a.hidden = p->hidden; a.flow = p->flow;
+  a.addend = p->addend; a.addend_stride = p->addend_stride;
+  a.w_rows_per_sample = p->w_rows_per_sample;
   a.ab_fmt = p->dtype == PFB_F16 ? 0 : 1;
   const size_t smem = (size_t)a.a_stages * a.a_slot_bytes + (size_t)a.b_stages * a.b_slot_bytes + sizeof(ConvBars) + 1024;
   int groups = sm_count() / CG;

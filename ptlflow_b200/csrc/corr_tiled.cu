@@ -43,24 +43,24 @@ __device__ __forceinline__ unsigned short f32_to_half_bits<__nv_bfloat16>(float 
 
 constexpr int kTlWarps = 4;
 
+// The first version of this kernel (one loop over 120 (level, row, chunk) slots and one over 324 channels, level
+// geometry and blend weights fetched through shared memory with a per-lane level index) retired 1000 instructions per
+// query-warp and ran at 87 % issue utilisation with DRAM at 23 % (ncu r02b): instruction-bound.  Here the levels are
+// unrolled: a lane's (window row, chunk) slot and its (i, j) output positions are the same for every level and are
+// decoded once; per level only the scaled coordinates, one address and the four blend weights remain, all in registers.
 template <typename T, int R, int LEVELS>
-__global__ void __launch_bounds__(kTlWarps * 32) corr_lookup_tiled_kernel(const TiledLevels lv_param, const float* __restrict__ coords,
+__global__ void __launch_bounds__(kTlWarps * 32) corr_lookup_tiled_kernel(const TiledLevels lv, const float* __restrict__ coords,
                                                                           T* __restrict__ out, int nq, int out_stride) {
   constexpr int D = 2 * R + 2, K = 2 * R + 1, KK = K * K;
   constexpr int ROWP = 24;                 // staged window row: 3 chunks of 8 columns (48 bytes)
   constexpr int LVP = D * ROWP;            // halfs per staged level
   constexpr int PLANES = LEVELS * KK;
-  constexpr int SLOTS = LEVELS * D * 3;    // 16-byte chunks to fetch per query (some predicated off)
   constexpr int OUTP = (PLANES + 7) / 8 * 8;
+  constexpr int NPOS = (KK + 31) / 32;     // output positions per lane and level
+  static_assert(D * 3 <= 32, "one (window row, chunk) slot per lane");
   __shared__ __align__(16) unsigned short stage[kTlWarps][LEVELS * LVP];
   __shared__ __align__(16) unsigned short orow[kTlWarps][OUTP];
-  __shared__ float wts[kTlWarps][LEVELS][4];
-  __shared__ int offs[kTlWarps][LEVELS];
-  __shared__ TiledLevels slv;  // the level table is indexed with a per-lane level: shared memory, not a local-memory copy of the parameter
 
-  if (threadIdx.x == 0) slv = lv_param;
-  __syncthreads();
-  const TiledLevels& lv = slv;
   pdl_wait();     // coords / volume come from the previous kernels in the stream
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,72 +69,85 @@ __global__ void __launch_bounds__(kTlWarps * 32) corr_lookup_tiled_kernel(const 
   const float2 c = __ldg(reinterpret_cast<const float2*>(coords) + q);
   unsigned short* st = stage[warp];
 
-  // ---- phase 1: fetch the tile rows of all levels ----
-  uint4 v[(SLOTS + 31) / 32];
+  // ---- phase 1: lane = (window row j, chunk ck), the same slot in every level; all levels' loads in flight together ----
+  const int j1 = lane / 3, ck = lane - j1 * 3;
+  const bool slot = lane < D * 3;
+  uint4 v[LEVELS];
+  float w00[LEVELS], w10[LEVELS], w01[LEVELS], w11[LEVELS];
+  int off[LEVELS];
 #pragma unroll
-  for (int k = 0; k < (SLOTS + 31) / 32; ++k) {
-    const int s = lane + 32 * k;
-    v[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (s < SLOTS) {
-      const int l = s / (3 * D), rem = s - l * (3 * D);
-      const int j = rem / 3, ck = rem - j * 3;
-      const float sc = 1.0f / (float)(1 << l);
-      const float x = c.x * sc, y = c.y * sc;
-      const bool finite = (fabsf(x) < 1e7f) && (fabsf(y) < 1e7f);
-      const float xf = finite ? floorf(x) : -1e6f, yf = finite ? floorf(y) : -1e6f;
-      const int x0 = (int)xf - R, y0 = (int)yf - R;
-      const int o = x0 & 7;              // column of the window's first tap inside its tile (two's complement: floor mod)
-      const int yy = y0 + j, tcol = (x0 >> 3) + ck;
-      // the third chunk is touched only when the 10 taps starting at column o run past 16
-      const bool need = (ck < 2) || (o + D > 16);
-      if (need && yy >= 0 && yy < lv.h[l] && tcol >= 0 && tcol < lv.tiles_x[l]) {
-        const unsigned short* base = reinterpret_cast<const unsigned short*>(lv.ptr[l]) + (size_t)q * lv.map_elems[l];
-        const unsigned e = ((unsigned)(yy >> 2) * (unsigned)lv.tiles_x[l] + (unsigned)tcol) * 32u + (unsigned)(yy & 3) * 8u;
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(base + e));
-        const int nvalid = lv.w[l] - tcol * 8;  // columns of this chunk inside the map (pad columns may hold anything)
+  for (int l = 0; l < LEVELS; ++l) {
+    const float sc = 1.0f / (float)(1 << l);
+    const float x = c.x * sc, y = c.y * sc;
+    const bool finite = (fabsf(x) < 1e7f) && (fabsf(y) < 1e7f);
+    const float xf = finite ? floorf(x) : -1e6f, yf = finite ? floorf(y) : -1e6f;
+    const float fx = finite ? x - xf : 0.f, fy = finite ? y - yf : 0.f;
+    w00[l] = (1.f - fx) * (1.f - fy);
+    w10[l] = fx * (1.f - fy);
+    w01[l] = (1.f - fx) * fy;
+    w11[l] = fx * fy;
+    const int x0 = (int)xf - R, y0 = (int)yf - R;
+    const int o = x0 & 7;                  // column of the window's first tap inside its tile (two's complement: floor mod)
+    off[l] = o;
+    const int yy = y0 + j1, tcol = (x0 >> 3) + ck;
+    v[l] = make_uint4(0u, 0u, 0u, 0u);
+    // the third chunk is touched only when the 2r+2 taps starting at column o run past 16
+    if (slot && (ck < 2 || o + D > 16) && yy >= 0 && yy < lv.h[l] && tcol >= 0 && tcol < lv.tiles_x[l]) {
+      const unsigned short* base = reinterpret_cast<const unsigned short*>(lv.ptr[l]) + (size_t)q * lv.map_elems[l];
+      const unsigned e = ((unsigned)(yy >> 2) * (unsigned)lv.tiles_x[l] + (unsigned)tcol) * 32u + (unsigned)(yy & 3) * 8u;
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + e));
+      if (lv.w[l] & 7) {  // kernel-uniform: only maps whose width is not a multiple of 8 have pad columns (they may hold anything)
+        const int nvalid = lv.w[l] - tcol * 8;
         if (nvalid < 8) {
           u.x = nvalid >= 2 ? u.x : (nvalid == 1 ? (u.x & 0xFFFFu) : 0u);
           u.y = nvalid >= 4 ? u.y : (nvalid == 3 ? (u.y & 0xFFFFu) : 0u);
           u.z = nvalid >= 6 ? u.z : (nvalid == 5 ? (u.z & 0xFFFFu) : 0u);
           u.w = nvalid >= 8 ? u.w : (nvalid == 7 ? (u.w & 0xFFFFu) : 0u);
         }
-        v[k] = u;
       }
-      if (j == 0 && ck == 0) {  // one lane per level publishes the blend weights and the column offset
-        const float fx = finite ? x - xf : 0.f, fy = finite ? y - yf : 0.f;
-        wts[warp][l][0] = (1.f - fx) * (1.f - fy);
-        wts[warp][l][1] = fx * (1.f - fy);
-        wts[warp][l][2] = (1.f - fx) * fy;
-        wts[warp][l][3] = fx * fy;
-        offs[warp][l] = o;
-      }
+      v[l] = u;
     }
   }
+  if (slot) {
 #pragma unroll
-  for (int k = 0; k < (SLOTS + 31) / 32; ++k) {
-    const int s = lane + 32 * k;
-    if (s < SLOTS) *reinterpret_cast<uint4*>(st + s * 8) = v[k];  // slot s = (l * D + j) * 3 + ck  ->  l * LVP + j * ROWP + ck * 8
+    for (int l = 0; l < LEVELS; ++l) *reinterpret_cast<uint4*>(st + l * LVP + lane * 8) = v[l];  // j1 * ROWP + ck * 8 == lane * 8
   }
   __syncwarp();
 
-  // ---- phase 2: blend.  channel = l * KK + i * K + j, i <-> x offset (x-major) ----
+  // ---- phase 2: lane = output positions (i, j) = lane, lane + 32, ... of the (2r+1)^2 window, the same in every level.
+  // channel = l * KK + i * K + j, i <-> x offset (x-major, corr.py:43-47) ----
   unsigned short* ow = orow[warp];
-#pragma unroll 2
-  for (int ch = lane; ch < PLANES; ch += 32) {
-    const int l = ch / KK, rem = ch - l * KK;
-    const int i = rem / K, j = rem - i * K;
-    const unsigned short* w0 = st + l * LVP + j * ROWP + offs[warp][l] + i;
-    const float* ww = wts[warp][l];
-    const float r = ww[0] * half_bits_to_f32<T>(w0[0]) + ww[1] * half_bits_to_f32<T>(w0[1]) + ww[2] * half_bits_to_f32<T>(w0[ROWP]) +
-                    ww[3] * half_bits_to_f32<T>(w0[ROWP + 1]);
-    ow[ch] = f32_to_half_bits<T>(r);
+  int tap[NPOS];
+#pragma unroll
+  for (int k = 0; k < NPOS; ++k) {
+    const int pos = lane + 32 * k;
+    const int i = pos / K, j = pos - i * K;
+    tap[k] = j * ROWP + i;
+  }
+#pragma unroll
+  for (int l = 0; l < LEVELS; ++l) {
+    const unsigned short* sl = st + l * LVP + off[l];
+#pragma unroll
+    for (int k = 0; k < NPOS; ++k) {
+      const int pos = lane + 32 * k;
+      if (pos < KK) {
+        const unsigned short* w0 = sl + tap[k];
+        const float r = w00[l] * half_bits_to_f32<T>(w0[0]) + w10[l] * half_bits_to_f32<T>(w0[1]) + w01[l] * half_bits_to_f32<T>(w0[ROWP]) +
+                        w11[l] * half_bits_to_f32<T>(w0[ROWP + 1]);
+        ow[l * KK + pos] = f32_to_half_bits<T>(r);
+      }
+    }
   }
   if (lane < OUTP - PLANES) ow[PLANES + lane] = 0;
   __syncwarp();
   // ---- coalesced 16-byte stores of the output row (out_stride % 8 == 0; columns beyond OUTP are zero-filled) ----
   uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(out) + (size_t)q * out_stride);
   const int chunks = out_stride >> 3;
-  for (int k = lane; k < chunks; k += 32) dst[k] = (k < OUTP / 8) ? reinterpret_cast<const uint4*>(ow)[k] : make_uint4(0u, 0u, 0u, 0u);
+  const uint4* ow4 = reinterpret_cast<const uint4*>(ow);
+  static_assert(OUTP / 8 <= 64, "two rounds of 16-byte stores cover the output row");
+  if (lane < OUTP / 8) dst[lane] = ow4[lane];
+  if (lane + 32 < OUTP / 8) dst[lane + 32] = ow4[lane + 32];
+  for (int k = OUTP / 8 + lane; k < chunks; k += 32) dst[k] = make_uint4(0u, 0u, 0u, 0u);  // only when the caller's rows are wider
 }
 
 template <typename T>

@@ -254,8 +254,9 @@ corr_volume_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 //     ncu (r01) had the 4-warp epilogue at ~7000 clk per patch against ~1900 clk of HBM time.
 //   * pooled levels are means of the fp32 accumulators, rounded once (closer to the fp32 reference than re-rounding
 //     every level like the reference's half path does; also 2 conversions fewer per element), packed conversions.
-//   * level 0 leaves through one 5-D TMA bulk store per patch: box [2 tile rows][8 16-byte tile-row chunks][128 queries]
-//     staged conflict-free; level 1 is one full 64-byte tile per (query, patch) written with 16-byte stores.
+//   * level 0 leaves through one TMA bulk store per patch: box [2 tile rows][128 queries][128 bytes] (the two tiles a
+//     patch owns in a tile row are contiguous), 128-byte swizzled staging; level 1 is one full 64-byte tile per
+//     (query, patch) written with 16-byte stores.
 //   B operand ring: 3 stages of one 64-channel chunk of BOTH patches (32 KB).  224 KB of shared memory, one CTA per SM.
 struct __align__(8) CorrTBars {
   uint64_t a_full;
@@ -419,8 +420,10 @@ corr_volume_tiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             u.y = cvt_pack2<T>(__uint_as_float(r[e * 16 + txh * 8 + 2]) * scale, __uint_as_float(r[e * 16 + txh * 8 + 3]) * scale);
             u.z = cvt_pack2<T>(__uint_as_float(r[e * 16 + txh * 8 + 4]) * scale, __uint_as_float(r[e * 16 + txh * 8 + 5]) * scale);
             u.w = cvt_pack2<T>(__uint_as_float(r[e * 16 + txh * 8 + 6]) * scale, __uint_as_float(r[e * 16 + txh * 8 + 7]) * scale);
-            const int slot = ((rr >> 2) * 8 + txh * 4 + (rr & 3)) * 128 + row;
-            *reinterpret_cast<uint4*>(sCg + slot * 16) = u;
+            // staging = TMA box [tile row 2][query 128][128 bytes = the two tiles of that tile row], 128-byte swizzle:
+            // 16-byte chunk (tile column txh, row-in-tile rr & 3) of query `row` sits at chunk index ^ (row & 7)
+            const int cidx = (txh * 4 + (rr & 3)) ^ (row & 7);
+            *reinterpret_cast<uint4*>(sCg + (((rr >> 2) * 128 + row) * 128 + cidx * 16)) = u;
           }
         }
         // ---- pooled levels from the fp32 accumulators (one rounding per stored value) ----
@@ -479,8 +482,8 @@ corr_volume_tiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       fence_proxy_async();               // generic-proxy writes -> visible to the async (TMA) proxy
       named_barrier_sync(1 + grp, 128);  // the four warps of this group
       if (leader && p_ok) {
-        // dims (8 elements, query, 16-byte chunk along the tile row, tile row, sample): clipped at N1 / tiles by the TMA unit
-        tma_store_5d(&tmO, sCg, 0, m_tile * 128, pw * 8, ph * 2, b);
+        // dims (element along the tile row, query, tile row, sample): clipped at the map / N1 by the TMA unit
+        tma_store_4d(&tmO, sCg, pw * 64, m_tile * 128, ph * 2, b);
         tma_store_commit();
       }
     }
@@ -592,11 +595,15 @@ int corr_volume_tiled(const void* f1, const void* f2, void* const* pyr, int B, i
     out.map_elems[l] = (unsigned)(((out.h[l] + 3) >> 2) * out.tiles_x[l] * 32);
   }
   {
+    // level-0 store map: a tile row of a query's map is tiles_x * 64 contiguous bytes, so the two tiles a patch owns in one
+    // tile row are ONE 128-byte run: box = [2 tile rows][128 queries][128 bytes], swizzled like an operand tile so that
+    // the per-thread 16-byte staging stores are conflict-free.  (The first version used 16-byte inner rows -- 2048 TMA
+    // requests per 32 KB box -- and ran at 1.56 TB/s; ncu r02b.)
     const uint64_t tx0 = (uint64_t)out.tiles_x[0], ty0 = (uint64_t)((H + 3) >> 2), map_bytes = ty0 * tx0 * 64;
-    uint64_t dims[5] = {8, (uint64_t)N1, 4 * tx0, ty0, (uint64_t)B};
-    uint64_t str[4] = {map_bytes, 16, 64 * tx0, (uint64_t)N1 * map_bytes};
-    uint32_t box[5] = {8, 128, 8, 2, 1};
-    int rc = make_tensor_map_linear(&tmO, pyr[0], dt, 5, dims, str, box);
+    uint64_t dims[4] = {32 * tx0, (uint64_t)N1, ty0, (uint64_t)B};
+    uint64_t str[3] = {map_bytes, 64 * tx0, (uint64_t)N1 * map_bytes};
+    uint32_t box[4] = {64, 128, 2, 1};
+    int rc = make_tensor_map(&tmO, pyr[0], dt, 4, dims, str, box);
     if (rc) return rc;
   }
   const int m_tiles = ceil_div(N1, 128);

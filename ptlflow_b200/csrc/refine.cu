@@ -10,6 +10,12 @@
 
 #include "common.cuh"
 
+#define PFB_TRY(expr)        \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != PFB_OK) return rc__; \
+  } while (0)
+
 namespace pfb {
 
 int launch_flow_from_coords(const float* coords, float* flow, int B, int H, int W, cudaStream_t s);
@@ -20,6 +26,7 @@ struct Workspace {
   size_t off_corr, off_cor1, off_corflo, off_flo1, off_motion, off_z, off_rh, off_fh, off_mh, off_mask, off_flow;
   size_t off_taps;          // flow head conv2 per-tap products [P][32] fp32 (tensor-core path)
   size_t off_vbuf, off_vT;  // gma: to_v(motion) [P][128] and its per-sample transpose [B][128][n_pad]
+  size_t off_ctx[4];        // iteration-invariant context terms of the GRU gates: zr1 [P][2hd], q1 [P][hd], zr2, q2 (tensor path)
   int n_pad;
   size_t total;
   int c_cor1, c_corflo, c_cor2, c_flo1, c_flo2, c_motion, c_fh;
@@ -58,6 +65,8 @@ static Workspace plan(const pfb_raft_cfg* c) {
   w.n_pad = (int)align_up((size_t)c->H * c->W, 64);
   w.off_vbuf = take(c->variant == 2 ? P * 128 * es : 0);
   w.off_vT = take(c->variant == 2 ? (size_t)c->B * 128 * w.n_pad * es : 0);
+  for (int i = 0; i < 4; ++i)
+    w.off_ctx[i] = take((c->variant != 1 && c->dtype != PFB_F32) ? P * (size_t)((i & 1) ? c->hidden_dim : 2 * c->hidden_dim) * es : 0);
   w.total = off;
   return w;
 }
@@ -96,7 +105,7 @@ static pfb_conv_src src_of(const void* ptr, int channels, int stride, int offset
 }
 
 static int run_conv(const Ctx& x, int layer, std::initializer_list<pfb_conv_src> srcs, int epi, void* out,
-                    int out_stride, int out_offset, float scale = 1.f) {
+                    int out_stride, int out_offset, float scale = 1.f, const void* addend = nullptr, int addend_stride = 0) {
   const pfb_layer& L = x.w->layers[layer];
   PFB_CHECK_ARG(L.weight, "raft: layer %d has no packed weight", layer);
   pfb_conv_params p{};
@@ -114,14 +123,31 @@ static int run_conv(const Ctx& x, int layer, std::initializer_list<pfb_conv_src>
   p.coords = x.b->coords; p.flow = reinterpret_cast<const float*>(x.at(x.ws.off_flow));
   p.dtype = x.c->dtype; p.impl = x.c->impl;
   p.weight_k = L.weight_k; p.Cin_pad = L.Cin_pad; p.Cout_pad_k = L.Cout_pad_k;
+  p.addend = addend; p.addend_stride = addend_stride;
   return pfb_conv2d(&p, (pfb_stream)x.s);
 }
 
-#define PFB_TRY(expr)        \
-  do {                       \
-    int rc__ = (expr);       \
-    if (rc__ != PFB_OK) return rc__; \
-  } while (0)
+// round-2 restructurings of the tensor-core path; PFB_GRU_CTX_SPLIT=0 / PFB_MERGE_C2F2=0 fall back to the plain layers
+static bool tensor_path(const Ctx& x) { return x.c->variant != 1 && x.c->dtype != PFB_F32 && x.c->impl != 1; }
+static bool ctx_split_active(const Ctx& x) {
+  static const int env = getenv("PFB_GRU_CTX_SPLIT") ? atoi(getenv("PFB_GRU_CTX_SPLIT")) : 1;
+  return env && tensor_path(x) && x.w->layers[PFB_L_GRUX_ZR1].weight_k && x.w->layers[PFB_L_CTX_ZR1].weight_k;
+}
+static bool merged_c2f2_active(const Ctx& x) {
+  static const int env = getenv("PFB_MERGE_C2F2") ? atoi(getenv("PFB_MERGE_C2F2")) : 1;
+  return env && tensor_path(x) && x.w->layers[PFB_L_CONVC2F2].weight_k;
+}
+// conv_inp(inp) + bias for the four GRU convolutions: once per forward (inp does not change over the iterations)
+static int run_context_terms(const Ctx& x) {
+  if (!ctx_split_active(x)) return PFB_OK;
+  const int hd = x.c->hidden_dim, cd = x.c->context_dim;
+  const int layers[4] = {PFB_L_CTX_ZR1, PFB_L_CTX_Q1, PFB_L_CTX_ZR2, PFB_L_CTX_Q2};
+  for (int i = 0; i < 4; ++i) {
+    const int n = (i & 1) ? hd : 2 * hd;
+    PFB_TRY(run_conv(x, layers[i], {src_of(x.b->inp, cd, cd)}, PFB_EPI_LINEAR, x.at(x.ws.off_ctx[i]), n, 0));
+  }
+  return PFB_OK;
+}
 
 static int lookup(const Ctx& x) {
   const pfb_raft_cfg* c = x.c;
@@ -151,10 +177,11 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
   float* flow = reinterpret_cast<float*>(x.at(ws.off_flow));
 
   // ---- motion encoder (update.py:76-112) ----
+  const bool merged_c2f2 = merged_c2f2_active(x);
   if (c->variant != 1) {
     void* cor1 = x.at(ws.off_cor1);
     PFB_TRY(run_conv(x, PFB_L_CONVC1, {src_of(corr, ws.planes, corr_stride)}, PFB_EPI_RELU, cor1, ws.c_cor1, 0));
-    PFB_TRY(run_conv(x, PFB_L_CONVC2, {src_of(cor1, ws.c_cor1, ws.c_cor1)}, PFB_EPI_RELU, corflo, ws.c_corflo, 0));
+    if (!merged_c2f2) PFB_TRY(run_conv(x, PFB_L_CONVC2, {src_of(cor1, ws.c_cor1, ws.c_cor1)}, PFB_EPI_RELU, corflo, ws.c_corflo, 0));
   } else {
     PFB_TRY(run_conv(x, PFB_L_CONVC1, {src_of(corr, ws.planes, corr_stride)}, PFB_EPI_RELU, corflo, ws.c_corflo, 0));
   }
@@ -166,7 +193,11 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
     else
       PFB_TRY(run_conv(x, PFB_L_CONVF1, {src_of(flow, 2, 2, 0, 1)}, PFB_EPI_RELU, flo1, ws.c_flo1, 0));
   }
-  PFB_TRY(run_conv(x, PFB_L_CONVF2, {src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU, corflo, ws.c_corflo, ws.c_cor2));
+  if (merged_c2f2)  // convc2 | convf2 as one block-diagonal layer: [cor1 (256) | flo1 (128)] -> [cor (192) | flo (64)]
+    PFB_TRY(run_conv(x, PFB_L_CONVC2F2, {src_of(x.at(ws.off_cor1), ws.c_cor1, ws.c_cor1), src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU,
+                     corflo, ws.c_corflo, 0));
+  else
+    PFB_TRY(run_conv(x, PFB_L_CONVF2, {src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU, corflo, ws.c_corflo, ws.c_cor2));
   PFB_TRY(run_conv(x, PFB_L_CONV, {src_of(corflo, ws.c_corflo, ws.c_corflo)}, PFB_EPI_RELU_APPEND_FLOW, motion, ws.c_motion, 0));
 
   // ---- gma: motion_global = motion + gamma * (attention @ to_v(motion))   gma_utils.py:101-113, gma/update.py:149 ----
@@ -179,6 +210,26 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
     PFB_TRY(run_conv(x, PFB_L_AGG_V, {src_of(motion, 128, ws.c_motion)}, PFB_EPI_LINEAR, vbuf, 128, 0));
     const bool tensor_path = c->dtype != PFB_F32 && c->impl != 1 && (N % 8) == 0;
     if (tensor_path) PFB_TRY(pfb_transpose_pm(vbuf, vT, c->B, N, 128, ws.n_pad, c->dtype, (pfb_stream)x.s));
+    static const int env_batched = getenv("PFB_GMA_BATCHED") ? atoi(getenv("PFB_GMA_BATCHED")) : 1;
+    if (tensor_path && env_batched) {
+      // ONE launch for all samples: pixels = queries, input channels = the N attention columns, per-sample weights = that
+      // sample's v^T (K-major [128][n_pad], rows b * 128 ...).  B x 55 row tiles fill the machine; one launch per sample left
+      // 55 of 148 SMs busy.
+      pfb_conv_params p{};
+      p.src[0] = src_of(x.b->attention, N, N);
+      p.nsrc = 1;
+      p.B = c->B; p.H = c->H; p.W = c->W; p.KH = 1; p.KW = 1;
+      p.Cout = 128; p.Cout_pad = 128;
+      p.weight = vbuf;  // (SIMT layout, unused on this path)
+      p.bias = nullptr;
+      p.epilogue = PFB_EPI_AXPY; p.scale = x.b->agg_gamma;
+      p.out = motion; p.out_stride = ws.c_motion; p.out_offset = 128;
+      p.aux_h = motion; p.hidden = ws.c_motion;
+      p.dtype = c->dtype; p.impl = 2;
+      p.weight_k = vT; p.Cin_pad = ws.n_pad; p.Cout_pad_k = 128;
+      p.w_rows_per_sample = 128;
+      PFB_TRY(pfb_conv2d(&p, (pfb_stream)x.s));
+    } else
     for (int b = 0; b < c->B; ++b) {
       // one "1x1 convolution" per sample: pixels = queries, input channels = the N attention columns,
       // weights = this sample's v (SIMT layout [N][128]) / v^T (K-major [128][n_pad])
@@ -201,7 +252,17 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
 
   // ---- GRU (update.py:24-32 ConvGRU, :58-73 SepConvGRU); x = [inp, motion (, motion_global)] ----
   const int halves = (c->variant != 1) ? 2 : 1;
+  const bool split = ctx_split_active(x);
   for (int h = 0; h < halves; ++h) {
+    if (split) {
+      // conv([h | inp | motion]) = conv_inp(inp) + bias (once per forward, run_context_terms) + conv_rest([h | motion]) (here)
+      const int lzr = h == 0 ? PFB_L_GRUX_ZR1 : PFB_L_GRUX_ZR2, lq = h == 0 ? PFB_L_GRUX_Q1 : PFB_L_GRUX_Q2;
+      PFB_TRY(run_conv(x, lzr, {src_of(x.b->net, hd, hd), src_of(motion, ws.c_motion, ws.c_motion)}, PFB_EPI_GRU_ZR, rh, hd, 0, 1.f,
+                       x.at(ws.off_ctx[2 * h]), 2 * hd));
+      PFB_TRY(run_conv(x, lq, {src_of(rh, hd, hd), src_of(motion, ws.c_motion, ws.c_motion)}, PFB_EPI_GRU_Q, x.b->net, hd, 0, 1.f,
+                       x.at(ws.off_ctx[2 * h + 1]), hd));
+      continue;
+    }
     const int lzr = h == 0 ? PFB_L_GRU_ZR1 : PFB_L_GRU_ZR2, lq = h == 0 ? PFB_L_GRU_Q1 : PFB_L_GRU_Q2;
     PFB_TRY(run_conv(x, lzr, {src_of(x.b->net, hd, hd), src_of(x.b->inp, cd, cd), src_of(motion, ws.c_motion, ws.c_motion)},
                      PFB_EPI_GRU_ZR, rh, hd, 0));
@@ -258,6 +319,7 @@ extern "C" PFB_API int pfb_raft_update_iter(const pfb_raft_cfg* cfg, const pfb_r
   Ctx x;
   PFB_TRY(make_ctx(x, cfg, w, buf, as_stream(stream), corr == nullptr));
   PFB_TRY(launch_flow_from_coords(buf->coords, reinterpret_cast<float*>(x.at(x.ws.off_flow)), cfg->B, cfg->H, cfg->W, x.s));
+  PFB_TRY(run_context_terms(x));
   if (!corr) PFB_TRY(lookup(x));
   return update_iter(x, corr, mask_out);
 }
@@ -270,6 +332,7 @@ extern "C" PFB_API int pfb_raft_refine(const pfb_raft_cfg* cfg, const pfb_raft_w
   PFB_CHECK_ARG(cfg->variant == 1 || cfg->iters >= 1, "raft_refine: the convex upsample needs at least one iteration (mask)");
   PFB_TRY(launch_flow_from_coords(buf->coords, reinterpret_cast<float*>(x.at(x.ws.off_flow)), cfg->B, cfg->H, cfg->W, x.s));
   void* mask = cfg->variant != 1 ? x.at(x.ws.off_mask) : nullptr;
+  PFB_TRY(run_context_terms(x));
   for (int it = 0; it < cfg->iters; ++it) {
     PFB_TRY(lookup(x));
     PFB_TRY(update_iter(x, nullptr, it == cfg->iters - 1 ? mask : nullptr));

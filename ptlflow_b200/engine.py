@@ -57,6 +57,32 @@ class RaftEngine:
             layers[_lib.L_GRU_Q1] = P(gsrc, gru.convq1)
             layers[_lib.L_GRU_ZR2] = P(gsrc, gru.convz2, gru.convr2)
             layers[_lib.L_GRU_Q2] = P(gsrc, gru.convq2)
+            if dtype != torch.float32:
+                # round 2: (a) the context columns of the four GRU convolutions become layers of their own, evaluated once per
+                # forward with the bias folded in, and the per-iteration layers lose them (-1/3 of the GRU's K); (b) convc2 |
+                # convf2 as one block-diagonal N = 256 layer.  Pure repacking of the same parameters.
+                class _View:
+                    def __init__(self, weight, bias):
+                        self.weight, self.bias = weight, bias
+
+                def cols(conv, lo, hi, with_bias):
+                    return _View(conv.weight.detach()[:, lo:hi].contiguous(), conv.bias if with_bias else None)
+
+                def rest(conv):  # [h | inp | motion...] without the inp columns
+                    w = conv.weight.detach()
+                    return _View(torch.cat([w[:, :hd], w[:, hd + cd:]], dim=1).contiguous(), None)
+
+                xsrc = [hd, gsrc[2]]
+                for ctx_id, x_id, convs in ((_lib.L_CTX_ZR1, _lib.L_GRUX_ZR1, (gru.convz1, gru.convr1)), (_lib.L_CTX_Q1, _lib.L_GRUX_Q1, (gru.convq1,)),
+                                            (_lib.L_CTX_ZR2, _lib.L_GRUX_ZR2, (gru.convz2, gru.convr2)), (_lib.L_CTX_Q2, _lib.L_GRUX_Q2, (gru.convq2,))):
+                    layers[ctx_id] = P([cd], *[cols(cv, hd, hd + cd, True) for cv in convs])
+                    layers[x_id] = P(xsrc, *[rest(cv) for cv in convs])
+                wc, wf = enc.convc2.weight.detach(), enc.convf2.weight.detach()
+                if tuple(wc.shape[2:]) == tuple(wf.shape[2:]) and wc.shape[0] + wf.shape[0] == 256:
+                    bd = torch.zeros((256, wc.shape[1] + wf.shape[1]) + tuple(wc.shape[2:]), dtype=wc.dtype, device=wc.device)
+                    bd[: wc.shape[0], : wc.shape[1]] = wc
+                    bd[wc.shape[0]:, wc.shape[1]:] = wf
+                    layers[_lib.L_CONVC2F2] = P([wc.shape[1], wf.shape[1]], _View(bd, torch.cat([enc.convc2.bias.detach(), enc.convf2.bias.detach()])))
             layers[_lib.L_FLOW1] = P([hd], fh.conv1)
             layers[_lib.L_FLOW2] = P([256], fh.conv2)
             if dtype != torch.float32:
