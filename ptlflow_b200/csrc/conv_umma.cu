@@ -83,10 +83,18 @@ struct ConvUmmaArgs {
 
 #define PFB_TR(slot) do { if (a.trace && lane == 0) a.trace[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
 
+// two fp32 -> one packed pair of the storage type: a single cvt.rn.{f16x2,bf16x2}.f32 (the epilogues convert 256 values per row)
 template <typename T>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  T lo = from_f32<T>(a), hi = from_f32<T>(b);
-  return (uint32_t)(*reinterpret_cast<uint16_t*>(&lo)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi)) << 16);
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 template <typename T>
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {

@@ -89,6 +89,8 @@ def _fold(conv: nn.Conv2d, norm: nn.Module, dtype, device):
 
 
 _NATIVE_CONV1 = bool(int(os.environ.get("PFB_NATIVE_CONV1", "1")))
+# batch-norm-folded convolutions without a residual join: cuDNN's own conv + bias + ReLU epilogue instead of a separate pass
+_CUDNN_FUSED_RELU = bool(int(os.environ.get("PFB_CUDNN_FUSED_RELU", "0")))
 _prep_lock = threading.Lock()
 
 
@@ -173,6 +175,11 @@ class _Encoder(nn.Module):
         prep = self._prepared(x.dtype, x.device)
 
         def conv_act(x, wb, stride, padding, relu=True, residual=None):
+            if _CUDNN_FUSED_RELU and not inst and relu and residual is None and x.dtype != torch.float32:
+                bh = wb[2] if len(wb) > 2 else wb[1].to(x.dtype)
+                y = torch.cudnn_convolution_relu(x.permute(0, 3, 1, 2), wb[0], bh, (stride, stride), (padding, padding), (1, 1), 1)
+                y = y.permute(0, 2, 3, 1)
+                return y if y.is_contiguous() else y.contiguous()
             y = _conv_pm(x, wb, stride, padding)
             if inst:
                 return ops.instance_norm_act(y, relu=relu, residual=residual, out=y)
