@@ -90,7 +90,7 @@ def _fold(conv: nn.Conv2d, norm: nn.Module, dtype, device):
 
 _NATIVE_CONV1 = bool(int(os.environ.get("PFB_NATIVE_CONV1", "1")))
 # batch-norm-folded convolutions without a residual join: cuDNN's own conv + bias + ReLU epilogue instead of a separate pass
-_CUDNN_FUSED_RELU = bool(int(os.environ.get("PFB_CUDNN_FUSED_RELU", "0")))
+_CUDNN_FUSED_RELU = bool(int(os.environ.get("PFB_CUDNN_FUSED_RELU", "1")))
 _prep_lock = threading.Lock()
 
 
