@@ -78,6 +78,7 @@ struct ConvUmmaArgs {
   const void* addend;            // optional per-pixel pre-activation term [B*H*W][addend_stride] (storage type), added instead of the bias
   int addend_stride;
   int ab_fmt;
+  int tma_out;                   // 1: outputs leave through shared-memory staging + TMA bulk stores (tmO0 = out, tmO1 = aux_z)
   unsigned long long* trace;     // debug timeline (PFB_CONV_TRACE): 32 clock64 slots per CTA, null in production
 };
 
@@ -155,12 +156,19 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint32_t a_lo, uint32_t a
 template <typename T, int CG>
 __global__ void __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                 const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW, const ConvUmmaArgs a) {
+                 const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const ConvUmmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + a.a_stages * a.a_slot_bytes;
-  ConvBars* bars = reinterpret_cast<ConvBars*>(smemB + a.b_stages * a.b_slot_bytes);
+  // output staging: 2 x [128 pixels][64 channels] (16 KB each), 128-byte swizzled like an operand tile.  The epilogue's
+  // thread <-> pixel mapping makes every direct global access a 16-byte piece per lane at a 256..768-byte stride (32 sectors
+  // per instruction, half of each used): the per-CTA timelines had the N = 256 epilogues at 4.5-8.4 us per tile, longer
+  // than the tile's MMAs once the GRU lost its context third.  Staged, the stores are conflict-free 16-byte shared-memory
+  // writes and the global side is the TMA unit writing whole 128-byte rows.
+  uint8_t* smemO = smemB + a.b_stages * a.b_slot_bytes;
+  ConvBars* bars = reinterpret_cast<ConvBars*>(smemO + (a.tma_out ? 2 * kATileBytes : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (a.trace && threadIdx.x == 0) {
@@ -196,6 +204,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tm0);
     prefetch_tmap(&tmW);
+    if (a.tma_out) prefetch_tmap(&tmO0);
   }
   tc_fence_before();
   __syncthreads();
@@ -359,6 +368,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     const int row = quarter * 32 + lane;
     const int hd = a.hidden;
     int i = 0;
+    unsigned blk = 0;  // running count of 64-column output blocks (staging buffer = blk & 1)
     for (int w = group0; w < a.n_work; w += group_stride, ++i) {
       int n0, b, y0, x0;
       decode(w, n0, b, y0, x0);
@@ -409,7 +419,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       // to v[], and completes under the arithmetic and the stores of chunk c.
       uint32_t r[32];
       if (group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
-      for (int c = group * 32; c < a.NT; c += 64) {
+      // 32 packed values -> this thread's half (group) of its pixel's 128-byte row in the staging buffer of block `blk`
+      auto stage32 = [&](const float (&v)[32]) {
+        uint8_t* sb = smemO + (blk & 1) * kATileBytes + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack2<T>(v[8 * q + 0], v[8 * q + 1]);
+          u.y = pack2<T>(v[8 * q + 2], v[8 * q + 3]);
+          u.z = pack2<T>(v[8 * q + 4], v[8 * q + 5]);
+          u.w = pack2<T>(v[8 * q + 6], v[8 * q + 7]);
+          *reinterpret_cast<uint4*>(sb + (((group * 4 + q) ^ (row & 7)) << 4)) = u;
+        }
+      };
+      for (int cb = 0; cb < a.NT; cb += 64) {
+       const int c = cb + group * 32;
+       if (c < a.NT) {  // (the last block of an NT % 64 == 32 tile has no chunk for group 1, which still joins the barrier below)
         const int n = n0 + c;  // first output channel of this chunk
         float v[32];
         uint4 hraw[4], zraw[4];
@@ -445,19 +470,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           if (aux_h_any) issue_aux(c + 64, hnext, znext);
           issue_add(c + 64, anext);
         }
-        if (!ok) continue;
+        if (ok || a.tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)
         T* out = reinterpret_cast<T*>(a.out);
         switch (a.epilogue) {
           case PFB_EPI_LINEAR: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] *= a.scale;
-            store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (a.tma_out) stage32(v);
+            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_RELU: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
-            store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (a.tma_out) stage32(v);
+            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_LINEAR_F32: {  // fp32 output (16-byte aligned rows: out_stride % 4 == 0)
@@ -480,7 +507,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[8 * q + e] = h[e] + a.scale * v[8 * q + e];
             }
-            store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (a.tma_out) stage32(v);
+            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_RELU_APPEND_FLOW: {
@@ -496,14 +524,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
               }
               valid += 2;
             }
-            store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
+            if (a.tma_out) stage32(v);  // (the store map ends after the two flow columns)
+            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
             break;
           }
           case PFB_EPI_GRU_ZR: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = __fdividef(1.f, 1.f + __expf(-v[e]));  // sigmoid: 2 MUFU ops
             if (n < hd) {
-              store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
+              if (a.tma_out) stage32(v);
+              else store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -512,7 +542,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[8 * q + e] *= h[e];
               }
-              store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
+              if (a.tma_out) stage32(v);
+              else store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
             }
             break;
           }
@@ -529,12 +560,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 v[8 * q + e] = (1.f - z[e]) * h[e] + z[e] * th;
               }
             }
-            store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
+            if (a.tma_out) stage32(v);
+            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
             break;
           }
           default:
             break;
         }
+        }
+       }
+       if (a.tma_out) {
+         // one 64-column block staged by both epilogue groups -> one bulk store.  Thread 0 first makes sure every store it has
+         // issued so far has drained its staging buffer, so that after the barrier the OTHER buffer may be overwritten.
+         fence_proxy_async();
+         if (threadIdx.x == 0) tma_store_wait_read();
+         named_barrier_sync(1, 256);
+         if (threadIdx.x == 0) {
+           const int nb = n0 + cb;
+           const void* sb = smemO + (blk & 1) * kATileBytes;
+           if (a.epilogue == PFB_EPI_GRU_ZR && nb < hd) tma_store_4d(&tmO1, sb, nb, x0, y0, b);
+           else tma_store_4d(&tmO0, sb, a.out_offset + (a.epilogue == PFB_EPI_GRU_ZR ? nb - hd : nb), x0, y0, b);
+           tma_store_commit();
+         }
+         ++blk;
+       }
       }
       tc_fence_before();
       __syncwarp();
@@ -546,6 +595,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       }
     }
   }
+  if (a.tma_out && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete (not only read)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) PFB_TR(18);
@@ -602,8 +652,8 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
 }
 
 template <typename T, int CG>
-static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const ConvUmmaArgs& a, int grid, size_t smem,
-                            cudaStream_t s) {
+static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const CUtensorMap* tmO, const ConvUmmaArgs& a, int grid,
+                            size_t smem, cudaStream_t s) {
   // once per (instantiation, device): correct when one process drives several devices, and off the per-launch path
   static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
@@ -626,7 +676,7 @@ static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, cons
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  PFB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, CG>, tms[0], tms[1], tms[2], tmW, a));
+  PFB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, CG>, tms[0], tms[1], tms[2], tmW, tmO[0], tmO[1], a));
   return PFB_OK;
 }
 
@@ -703,19 +753,46 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.a_slot_bytes = (int)align_up((size_t)a.a_tx_bytes, 1024);
   a.b_tap_bytes = (a.NT / CG) * 128;
   {
+    static const int env_tma_out = getenv("PFB_CONV_TMA_STORE") ? atoi(getenv("PFB_CONV_TMA_STORE")) : 1;
+    a.tma_out = env_tma_out && p->epilogue != PFB_EPI_LINEAR_F32 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
+                (p->epilogue != PFB_EPI_GRU_ZR || (p->hidden % 64 == 0 && (reinterpret_cast<uintptr_t>(p->aux_z) & 15) == 0));
+  }
+  const int ring_budget = (a.tma_out ? 180 : 212) * 1024;  // 2 x 16 KB of output staging come out of the rings' share
+  {
     static const int env_group = getenv("PFB_CONV_TAP_GROUP") ? atoi(getenv("PFB_CONV_TAP_GROUP")) : 1;
     const int taps = a.halo == 1 ? p->KW : (a.halo == 2 ? p->KH : 1);
     a.b_group = 1;
     // all taps of a patch in one weight stage when at least 3 such stages fit next to 3 activation patches
-    if (env_group && (taps == 3 || taps == 5) && 3 * taps * a.b_tap_bytes + 3 * a.a_slot_bytes <= 212 * 1024 && a.NT <= 192) a.b_group = taps;
+    if (env_group && (taps == 3 || taps == 5) && 3 * taps * a.b_tap_bytes + 3 * a.a_slot_bytes <= ring_budget && a.NT <= 192) a.b_group = taps;
   }
   a.b_slot_bytes = a.b_group * a.b_tap_bytes;
+  // ---- outputs through staging + TMA bulk stores (everything but the fp32 tap products) ----
+  CUtensorMap tmO[2];
+  tmO[0] = tms[0];
+  tmO[1] = tms[0];
+  {
+    const bool zr = p->epilogue == PFB_EPI_GRU_ZR;
+    if (a.tma_out) {
+      const int ncols = zr ? p->hidden : (p->epilogue == PFB_EPI_RELU_APPEND_FLOW ? p->Cout + 2 : p->Cout);
+      uint64_t dims[4] = {(uint64_t)(p->out_offset + ncols), (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+      uint64_t str[3] = {(uint64_t)p->out_stride * 2, (uint64_t)p->W * p->out_stride * 2, (uint64_t)p->H * p->W * p->out_stride * 2};
+      uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+      int rc = make_tensor_map(&tmO[0], p->out, p->dtype, 4, dims, str, box);
+      if (rc) return rc;
+      if (zr) {
+        uint64_t dz[4] = {(uint64_t)p->hidden, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+        uint64_t sz[3] = {(uint64_t)p->hidden * 2, (uint64_t)p->W * p->hidden * 2, (uint64_t)p->H * p->W * p->hidden * 2};
+        rc = make_tensor_map(&tmO[1], p->aux_z, p->dtype, 4, dz, sz, box);
+        if (rc) return rc;
+      }
+    }
+  }
   {
     // Split ~212 KB between the rings.  The per-CTA timelines (PFB_CONV_TRACE, profiles/r01_conv_trace_*.txt) show a
     // slot is reused only once per ~2.2 us (commit -> producer wake-up -> TMA round trip -> issue), so the number of
     // K steps in flight, not the bytes, sets the pace of the small-N layers: maximise min(steps covered by the
     // activation ring, weight stages).
-    const int budget = 212 * 1024;
+    const int budget = ring_budget;
     const int taps_per_patch = a.halo == 1 ? p->KW : (a.halo == 2 ? p->KH : 1);
     int best = -1;
     for (int as = 2; as <= kMaxAStages; ++as) {
@@ -733,7 +810,8 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.addend = p->addend; a.addend_stride = p->addend_stride;
   a.w_rows_per_sample = p->w_rows_per_sample;
   a.ab_fmt = p->dtype == PFB_F16 ? 0 : 1;
-  const size_t smem = (size_t)a.a_stages * a.a_slot_bytes + (size_t)a.b_stages * a.b_slot_bytes + sizeof(ConvBars) + 1024;
+  const size_t smem = (size_t)a.a_stages * a.a_slot_bytes + (size_t)a.b_stages * a.b_slot_bytes + (a.tma_out ? 2 * kATileBytes : 0) +
+                      sizeof(ConvBars) + 1024;
   int groups = sm_count() / CG;
   if (groups > a.n_work) groups = a.n_work;
   const int grid = groups * CG;
@@ -744,8 +822,8 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
     PFB_CUDA(cudaMemsetAsync(dbuf, 0, 256 * 32 * 8, s));
     a.trace = dbuf;
     int rc;
-    if (CG == 2) rc = p->dtype == PFB_F16 ? launch_conv_umma<__half, 2>(tms, tmW, a, grid, smem, s) : launch_conv_umma<__nv_bfloat16, 2>(tms, tmW, a, grid, smem, s);
-    else rc = p->dtype == PFB_F16 ? launch_conv_umma<__half, 1>(tms, tmW, a, grid, smem, s) : launch_conv_umma<__nv_bfloat16, 1>(tms, tmW, a, grid, smem, s);
+    if (CG == 2) rc = p->dtype == PFB_F16 ? launch_conv_umma<__half, 2>(tms, tmW, tmO, a, grid, smem, s) : launch_conv_umma<__nv_bfloat16, 2>(tms, tmW, tmO, a, grid, smem, s);
+    else rc = p->dtype == PFB_F16 ? launch_conv_umma<__half, 1>(tms, tmW, tmO, a, grid, smem, s) : launch_conv_umma<__nv_bfloat16, 1>(tms, tmW, tmO, a, grid, smem, s);
     if (rc) return rc;
     PFB_CUDA(cudaStreamSynchronize(s));
     static unsigned long long host[256 * 32];
@@ -761,11 +839,11 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   }
   ProfScope prof(KC_CONV, s);
   if (CG == 2) {
-    if (p->dtype == PFB_F16) return launch_conv_umma<__half, 2>(tms, tmW, a, grid, smem, s);
-    return launch_conv_umma<__nv_bfloat16, 2>(tms, tmW, a, grid, smem, s);
+    if (p->dtype == PFB_F16) return launch_conv_umma<__half, 2>(tms, tmW, tmO, a, grid, smem, s);
+    return launch_conv_umma<__nv_bfloat16, 2>(tms, tmW, tmO, a, grid, smem, s);
   }
-  if (p->dtype == PFB_F16) return launch_conv_umma<__half, 1>(tms, tmW, a, grid, smem, s);
-  return launch_conv_umma<__nv_bfloat16, 1>(tms, tmW, a, grid, smem, s);
+  if (p->dtype == PFB_F16) return launch_conv_umma<__half, 1>(tms, tmW, tmO, a, grid, smem, s);
+  return launch_conv_umma<__nv_bfloat16, 1>(tms, tmW, tmO, a, grid, smem, s);
 }
 
 }  // namespace pfb
