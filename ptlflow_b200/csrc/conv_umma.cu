@@ -35,6 +35,7 @@ namespace pfb {
 using namespace sm100;
 
 constexpr int kATileBytes = 128 * 128;
+constexpr int kMaxBias = 1024;  // output channels per layer whose bias is kept in shared memory (Cout_pad_k <= 1024)
 constexpr int kMaxAStages = 8, kMaxBStages = 32;
 
 struct __align__(8) ConvBars {
@@ -153,8 +154,10 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint32_t a_lo, uint32_t a
 // CG = 1: one CTA per MMA (M = 128).  CG = 2: CTA pairs (cta_group::2, M = 256): the pair shares every weight
 // tile -- each CTA stages only half of its rows and the tensor cores of both SMs read both halves -- which
 // halves the shared-memory traffic per MMA, the limiter of the single-CTA version.
-template <typename T, int CG>
-__global__ void __launch_bounds__(320, 1)
+// EPI (the pfb_epilogue) is a template parameter: with a run-time switch the register allocation of every epilogue was the
+// union of all of them (h, z, addend and bias operands live together), and the staged-store version spilled.
+template <typename T, int CG, int EPI>
+__global__ void __maxnreg__(200)  // 320 threads x 200 registers = 64000 of the SM's 65536 (ptxas stops at 168 under __launch_bounds__(320, 1))
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const ConvUmmaArgs a) {
@@ -162,13 +165,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + a.a_stages * a.a_slot_bytes;
-  // output staging: 2 x [128 pixels][64 channels] (16 KB each), 128-byte swizzled like an operand tile.  The epilogue's
+  // output staging: [128 pixels][64 channels] (16 KB), 128-byte swizzled like an operand tile, followed by the bias vector.  The epilogue's
   // thread <-> pixel mapping makes every direct global access a 16-byte piece per lane at a 256..768-byte stride (32 sectors
   // per instruction, half of each used): the per-CTA timelines had the N = 256 epilogues at 4.5-8.4 us per tile, longer
   // than the tile's MMAs once the GRU lost its context third.  Staged, the stores are conflict-free 16-byte shared-memory
   // writes and the global side is the TMA unit writing whole 128-byte rows.
   uint8_t* smemO = smemB + a.b_stages * a.b_slot_bytes;
-  ConvBars* bars = reinterpret_cast<ConvBars*>(smemO + (a.tma_out ? 2 * kATileBytes : 0));
+  float* sbias = reinterpret_cast<float*>(smemO + (a.tma_out ? kATileBytes : 0));  // n_tiles * NT <= kMaxBias floats
+  ConvBars* bars = reinterpret_cast<ConvBars*>(reinterpret_cast<uint8_t*>(sbias) + kMaxBias * sizeof(float));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (a.trace && threadIdx.x == 0) {
@@ -197,6 +201,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     }
     fence_barrier_init();
   }
+  // the bias vector is read by every epilogue thread for every 32-column chunk: one copy in shared memory instead of 8
+  // dependent global loads per chunk (11.6 % + 10.1 % of the convc1 launch's stall samples sat on them, ncu r02c)
+  for (int k = threadIdx.x; k < a.n_tiles * a.NT && k < kMaxBias; k += blockDim.x) sbias[k] = a.bias ? a.bias[k] : 0.f;
   if (warp == 5) {
     if (CG == 2) tmem_alloc_2cta<512>(&bars->tmem_base);
     else tmem_alloc<512>(&bars->tmem_base);
@@ -368,7 +375,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     const int row = quarter * 32 + lane;
     const int hd = a.hidden;
     int i = 0;
-    unsigned blk = 0;  // running count of 64-column output blocks (staging buffer = blk & 1)
     for (int w = group0; w < a.n_work; w += group_stride, ++i) {
       int n0, b, y0, x0;
       decode(w, n0, b, y0, x0);
@@ -380,14 +386,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       // of this tile, and the next chunk's while the current one is processed: the ncu source view of the first
       // version had the epilogue warps parked on these loads (exposed L2 latency, 25 % of their time), which made
       // the GRU layers epilogue-bound (3 tiles per CTA, each epilogue ~2x the tile's MMA time).
-      const bool aux_h_any = a.epilogue == PFB_EPI_GRU_ZR || a.epilogue == PFB_EPI_GRU_Q || a.epilogue == PFB_EPI_AXPY;
+      const bool aux_h_any = EPI == PFB_EPI_GRU_ZR || EPI == PFB_EPI_GRU_Q || EPI == PFB_EPI_AXPY;
       auto issue_aux = [&](int c, uint4 (&hq)[4], uint4 (&zq)[4]) {
         const int n = n0 + c;
-        const bool need_h = ok && ((a.epilogue == PFB_EPI_GRU_ZR && n >= hd) || a.epilogue == PFB_EPI_GRU_Q ||
-                                   (a.epilogue == PFB_EPI_AXPY && n + 32 <= a.Cout));
-        const bool need_z = ok && a.epilogue == PFB_EPI_GRU_Q;
+        const bool need_h = ok && ((EPI == PFB_EPI_GRU_ZR && n >= hd) || EPI == PFB_EPI_GRU_Q ||
+                                   (EPI == PFB_EPI_AXPY && n + 32 <= a.Cout));
+        const bool need_z = ok && EPI == PFB_EPI_GRU_Q;
         if (need_h) {
-          const T* hp = reinterpret_cast<const T*>(a.aux_h) + p * hd + (a.epilogue == PFB_EPI_GRU_ZR ? n - hd : n);
+          const T* hp = reinterpret_cast<const T*>(a.aux_h) + p * hd + (EPI == PFB_EPI_GRU_ZR ? n - hd : n);
 #pragma unroll
           for (int q = 0; q < 4; ++q) hq[q] = reinterpret_cast<const uint4*>(hp)[q];
         }
@@ -410,7 +416,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
       for (int q = 0; q < 4; ++q) hnext[q] = znext[q] = anext[q] = make_uint4(0u, 0u, 0u, 0u);
       if (aux_h_any) issue_aux(group * 32, hnext, znext);
-      issue_add(group * 32, anext);
+      // (the q epilogue already carries h and z one chunk ahead; its addend is requested at the top of its own chunk instead,
+      //  which keeps the kernel under the 200-register budget without spills)
+      constexpr bool kAddAhead = EPI != PFB_EPI_GRU_Q;
+      if (kAddAhead) issue_add(group * 32, anext);
       mbar_wait(&bars->acc_full[t], tuse & 1);
       tc_fence_after();
       if (warp == 0 && i < 3) PFB_TR(12 + i);
@@ -419,28 +428,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       // to v[], and completes under the arithmetic and the stores of chunk c.
       uint32_t r[32];
       if (group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
-      // 32 packed values -> this thread's half (group) of its pixel's 128-byte row in the staging buffer of block `blk`
-      auto stage32 = [&](const float (&v)[32]) {
-        uint8_t* sb = smemO + (blk & 1) * kATileBytes + row * 128;
+      // 32 packed values -> this thread's half (group) of its pixel's 128-byte row in the staging buffer
+      auto stage32 = [&](const uint4 (&pk)[4]) {
+        uint8_t* sb = smemO + row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack2<T>(v[8 * q + 0], v[8 * q + 1]);
-          u.y = pack2<T>(v[8 * q + 2], v[8 * q + 3]);
-          u.z = pack2<T>(v[8 * q + 4], v[8 * q + 5]);
-          u.w = pack2<T>(v[8 * q + 6], v[8 * q + 7]);
-          *reinterpret_cast<uint4*>(sb + (((group * 4 + q) ^ (row & 7)) << 4)) = u;
-        }
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(sb + (((group * 4 + q) ^ (row & 7)) << 4)) = pk[q];
       };
       for (int cb = 0; cb < a.NT; cb += 64) {
        const int c = cb + group * 32;
-       if (c < a.NT) {  // (the last block of an NT % 64 == 32 tile has no chunk for group 1, which still joins the barrier below)
+       uint4 pk[4];  // the chunk's 32 results, converted: what stays live across the staging barrier
+       if (c < a.NT) {
+        float v[32];  // (the last block of an NT % 64 == 32 tile has no chunk for group 1, which still joins the barriers below)
         const int n = n0 + c;  // first output channel of this chunk
-        float v[32];
         uint4 hraw[4], zraw[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) { hraw[q] = hnext[q]; zraw[q] = znext[q]; }
         if (addp) {  // warp-uniform: per-pixel addend instead of the per-channel bias
+          if (!kAddAhead) issue_add(c, anext);
           uint4 araw[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) araw[q] = anext[q];
@@ -455,7 +459,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         } else {
           float4 bb[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) bb[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < 8; ++q) bb[q] = reinterpret_cast<const float4*>(sbias + n)[q];
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -468,23 +472,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         if (c + 64 < a.NT) {  // warp-uniform
           tmem_ld_32x32(taddr + c + 64, r);
           if (aux_h_any) issue_aux(c + 64, hnext, znext);
-          issue_add(c + 64, anext);
+          if (kAddAhead) issue_add(c + 64, anext);
         }
         if (ok || a.tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)
         T* out = reinterpret_cast<T*>(a.out);
-        switch (a.epilogue) {
+        switch (EPI) {
           case PFB_EPI_LINEAR: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] *= a.scale;
-            if (a.tma_out) stage32(v);
-            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_RELU: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
-            if (a.tma_out) stage32(v);
-            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_LINEAR_F32: {  // fp32 output (16-byte aligned rows: out_stride % 4 == 0)
@@ -507,8 +509,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[8 * q + e] = h[e] + a.scale * v[8 * q + e];
             }
-            if (a.tma_out) stage32(v);
-            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_RELU_APPEND_FLOW: {
@@ -524,16 +525,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
               }
               valid += 2;
             }
-            if (a.tma_out) stage32(v);  // (the store map ends after the two flow columns)
-            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
+            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
             break;
           }
           case PFB_EPI_GRU_ZR: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = __fdividef(1.f, 1.f + __expf(-v[e]));  // sigmoid: 2 MUFU ops
             if (n < hd) {
-              if (a.tma_out) stage32(v);
-              else store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
+              if (!a.tma_out) store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -542,8 +541,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[8 * q + e] *= h[e];
               }
-              if (a.tma_out) stage32(v);
-              else store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
+              if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
             }
             break;
           }
@@ -560,29 +558,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 v[8 * q + e] = (1.f - z[e]) * h[e] + z[e] * th;
               }
             }
-            if (a.tma_out) stage32(v);
-            else store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
+            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
             break;
           }
           default:
             break;
         }
         }
+        if (a.tma_out) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            pk[q].x = pack2<T>(v[8 * q + 0], v[8 * q + 1]);
+            pk[q].y = pack2<T>(v[8 * q + 2], v[8 * q + 3]);
+            pk[q].z = pack2<T>(v[8 * q + 4], v[8 * q + 5]);
+            pk[q].w = pack2<T>(v[8 * q + 6], v[8 * q + 7]);
+          }
+        }
        }
        if (a.tma_out) {
-         // one 64-column block staged by both epilogue groups -> one bulk store.  Thread 0 first makes sure every store it has
-         // issued so far has drained its staging buffer, so that after the barrier the OTHER buffer may be overwritten.
-         fence_proxy_async();
+         // One 64-column block, staged by both epilogue groups, leaves as one bulk store (single staging buffer: the previous
+         // block's store has had this block's arithmetic to drain; thread 0 confirms it before anybody overwrites the buffer).
          if (threadIdx.x == 0) tma_store_wait_read();
+         named_barrier_sync(1, 256);
+         if (c < a.NT) stage32(pk);
+         fence_proxy_async();
          named_barrier_sync(1, 256);
          if (threadIdx.x == 0) {
            const int nb = n0 + cb;
-           const void* sb = smemO + (blk & 1) * kATileBytes;
-           if (a.epilogue == PFB_EPI_GRU_ZR && nb < hd) tma_store_4d(&tmO1, sb, nb, x0, y0, b);
-           else tma_store_4d(&tmO0, sb, a.out_offset + (a.epilogue == PFB_EPI_GRU_ZR ? nb - hd : nb), x0, y0, b);
+           if (EPI == PFB_EPI_GRU_ZR && nb < hd) tma_store_4d(&tmO1, smemO, nb, x0, y0, b);
+           else tma_store_4d(&tmO0, smemO, a.out_offset + (EPI == PFB_EPI_GRU_ZR ? nb - hd : nb), x0, y0, b);
            tma_store_commit();
          }
-         ++blk;
        }
       }
       tc_fence_before();
@@ -613,7 +619,7 @@ static int eff_channels(const pfb_conv_src& s) { return (int)align_up((size_t)s.
 
 bool conv2d_umma_supported(const pfb_conv_params* p) {
   if (p->dtype != PFB_F16 && p->dtype != PFB_BF16) return false;
-  if (!p->weight_k || p->Cout_pad_k < 16 || p->Cout_pad_k % 16) return false;
+  if (!p->weight_k || p->Cout_pad_k < 16 || p->Cout_pad_k % 16 || p->Cout_pad_k > kMaxBias) return false;
   if (p->nsrc > 3) return false;
   int cin_pad = 0;
   for (int i = 0; i < p->nsrc; ++i) {
@@ -651,15 +657,15 @@ bool conv2d_umma_supported(const pfb_conv_params* p) {
   return true;
 }
 
-template <typename T, int CG>
-static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const CUtensorMap* tmO, const ConvUmmaArgs& a, int grid,
-                            size_t smem, cudaStream_t s) {
+template <typename T, int CG, int EPI>
+static int launch_conv_umma_e(const CUtensorMap* tms, const CUtensorMap& tmW, const CUtensorMap* tmO, const ConvUmmaArgs& a, int grid,
+                              size_t smem, cudaStream_t s) {
   // once per (instantiation, device): correct when one process drives several devices, and off the per-launch path
   static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
   PFB_CUDA(cudaGetDevice(&dev));
   if (!(attr_done.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
-    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PFB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   cudaLaunchConfig_t cfg{};
@@ -676,8 +682,25 @@ static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, cons
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  PFB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, CG>, tms[0], tms[1], tms[2], tmW, tmO[0], tmO[1], a));
+  PFB_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, CG, EPI>, tms[0], tms[1], tms[2], tmW, tmO[0], tmO[1], a));
   return PFB_OK;
+}
+
+template <typename T, int CG>
+static int launch_conv_umma(const CUtensorMap* tms, const CUtensorMap& tmW, const CUtensorMap* tmO, const ConvUmmaArgs& a, int grid,
+                            size_t smem, cudaStream_t s) {
+  switch (a.epilogue) {
+    case PFB_EPI_LINEAR: return launch_conv_umma_e<T, CG, PFB_EPI_LINEAR>(tms, tmW, tmO, a, grid, smem, s);
+    case PFB_EPI_RELU: return launch_conv_umma_e<T, CG, PFB_EPI_RELU>(tms, tmW, tmO, a, grid, smem, s);
+    case PFB_EPI_GRU_ZR: return launch_conv_umma_e<T, CG, PFB_EPI_GRU_ZR>(tms, tmW, tmO, a, grid, smem, s);
+    case PFB_EPI_GRU_Q: return launch_conv_umma_e<T, CG, PFB_EPI_GRU_Q>(tms, tmW, tmO, a, grid, smem, s);
+    case PFB_EPI_RELU_APPEND_FLOW: return launch_conv_umma_e<T, CG, PFB_EPI_RELU_APPEND_FLOW>(tms, tmW, tmO, a, grid, smem, s);
+    case PFB_EPI_AXPY: return launch_conv_umma_e<T, CG, PFB_EPI_AXPY>(tms, tmW, tmO, a, grid, smem, s);
+    case PFB_EPI_LINEAR_F32: return launch_conv_umma_e<T, CG, PFB_EPI_LINEAR_F32>(tms, tmW, tmO, a, grid, smem, s);
+    default: break;
+  }
+  set_error("conv_umma: epilogue %d has no tensor-core instantiation", a.epilogue);
+  return PFB_ERR_UNSUPPORTED;
 }
 
 // M tile shape: TW x TH = 128 with the least padded area (ties -> the wider tile: fewer, longer TMA rows)
@@ -757,7 +780,7 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
     a.tma_out = env_tma_out && p->epilogue != PFB_EPI_LINEAR_F32 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
                 (p->epilogue != PFB_EPI_GRU_ZR || (p->hidden % 64 == 0 && (reinterpret_cast<uintptr_t>(p->aux_z) & 15) == 0));
   }
-  const int ring_budget = (a.tma_out ? 180 : 212) * 1024;  // 2 x 16 KB of output staging come out of the rings' share
+  const int ring_budget = (a.tma_out ? 192 : 208) * 1024;  // 16 KB of output staging + 4 KB of bias come out of the rings' share
   {
     static const int env_group = getenv("PFB_CONV_TAP_GROUP") ? atoi(getenv("PFB_CONV_TAP_GROUP")) : 1;
     const int taps = a.halo == 1 ? p->KW : (a.halo == 2 ? p->KH : 1);
@@ -810,8 +833,8 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.addend = p->addend; a.addend_stride = p->addend_stride;
   a.w_rows_per_sample = p->w_rows_per_sample;
   a.ab_fmt = p->dtype == PFB_F16 ? 0 : 1;
-  const size_t smem = (size_t)a.a_stages * a.a_slot_bytes + (size_t)a.b_stages * a.b_slot_bytes + (a.tma_out ? 2 * kATileBytes : 0) +
-                      sizeof(ConvBars) + 1024;
+  const size_t smem = (size_t)a.a_stages * a.a_slot_bytes + (size_t)a.b_stages * a.b_slot_bytes + (a.tma_out ? kATileBytes : 0) +
+                      kMaxBias * sizeof(float) + sizeof(ConvBars) + 1024;
   int groups = sm_count() / CG;
   if (groups > a.n_work) groups = a.n_work;
   const int grid = groups * CG;
