@@ -157,7 +157,7 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint32_t a_lo, uint32_t a
 // EPI (the pfb_epilogue) is a template parameter: with a run-time switch the register allocation of every epilogue was the
 // union of all of them (h, z, addend and bias operands live together), and the staged-store version spilled.
 template <typename T, int CG, int EPI>
-__global__ void __maxnreg__(200)  // 320 threads x 200 registers = 64000 of the SM's 65536 (ptxas stops at 168 under __launch_bounds__(320, 1))
+__global__ void __maxnreg__(192)  // 10 warps x 192 registers (allocated per warp in units of 512: 200 does not launch); ptxas stops at 168 under __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const ConvUmmaArgs a) {
@@ -387,18 +387,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       // version had the epilogue warps parked on these loads (exposed L2 latency, 25 % of their time), which made
       // the GRU layers epilogue-bound (3 tiles per CTA, each epilogue ~2x the tile's MMA time).
       const bool aux_h_any = EPI == PFB_EPI_GRU_ZR || EPI == PFB_EPI_GRU_Q || EPI == PFB_EPI_AXPY;
-      auto issue_aux = [&](int c, uint4 (&hq)[4], uint4 (&zq)[4]) {
+      auto issue_h = [&](int c, uint4 (&hq)[4]) {
         const int n = n0 + c;
-        const bool need_h = ok && ((EPI == PFB_EPI_GRU_ZR && n >= hd) || EPI == PFB_EPI_GRU_Q ||
-                                   (EPI == PFB_EPI_AXPY && n + 32 <= a.Cout));
-        const bool need_z = ok && EPI == PFB_EPI_GRU_Q;
+        const bool need_h = ok && ((EPI == PFB_EPI_GRU_ZR && n >= hd) || EPI == PFB_EPI_GRU_Q || (EPI == PFB_EPI_AXPY && n + 32 <= a.Cout));
         if (need_h) {
           const T* hp = reinterpret_cast<const T*>(a.aux_h) + p * hd + (EPI == PFB_EPI_GRU_ZR ? n - hd : n);
 #pragma unroll
           for (int q = 0; q < 4; ++q) hq[q] = reinterpret_cast<const uint4*>(hp)[q];
         }
-        if (need_z) {
-          const T* zp = reinterpret_cast<const T*>(a.aux_z) + p * hd + n;
+      };
+      auto issue_z = [&](int c, uint4 (&zq)[4]) {
+        if (ok && EPI == PFB_EPI_GRU_Q) {
+          const T* zp = reinterpret_cast<const T*>(a.aux_z) + p * hd + n0 + c;
 #pragma unroll
           for (int q = 0; q < 4; ++q) zq[q] = reinterpret_cast<const uint4*>(zp)[q];
         }
@@ -412,12 +412,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           for (int q = 0; q < 4; ++q) aq[q] = reinterpret_cast<const uint4*>(addp + c)[q];
         }
       };
-      uint4 hnext[4], znext[4], anext[4];
+      uint4 hnext[4], anext[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) hnext[q] = znext[q] = anext[q] = make_uint4(0u, 0u, 0u, 0u);
-      if (aux_h_any) issue_aux(group * 32, hnext, znext);
-      // (the q epilogue already carries h and z one chunk ahead; its addend is requested at the top of its own chunk instead,
-      //  which keeps the kernel under the 200-register budget without spills)
+      for (int q = 0; q < 4; ++q) hnext[q] = anext[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (aux_h_any) issue_h(group * 32, hnext);
+      // (the q epilogue carries h one chunk ahead; its z and addend are requested at the top of their own chunk instead,
+      //  which keeps the kernel inside the 192-register budget)
       constexpr bool kAddAhead = EPI != PFB_EPI_GRU_Q;
       if (kAddAhead) issue_add(group * 32, anext);
       mbar_wait(&bars->acc_full[t], tuse & 1);
@@ -441,8 +441,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         float v[32];  // (the last block of an NT % 64 == 32 tile has no chunk for group 1, which still joins the barriers below)
         const int n = n0 + c;  // first output channel of this chunk
         uint4 hraw[4], zraw[4];
+        issue_z(c, zraw);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { hraw[q] = hnext[q]; zraw[q] = znext[q]; }
+        for (int q = 0; q < 4; ++q) hraw[q] = hnext[q];
         if (addp) {  // warp-uniform: per-pixel addend instead of the per-channel bias
           if (!kAddAhead) issue_add(c, anext);
           uint4 araw[4];
@@ -471,7 +472,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         }
         if (c + 64 < a.NT) {  // warp-uniform
           tmem_ld_32x32(taddr + c + 64, r);
-          if (aux_h_any) issue_aux(c + 64, hnext, znext);
+          if (aux_h_any) issue_h(c + 64, hnext);
           if (kAddAhead) issue_add(c + 64, anext);
         }
         if (ok || a.tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)
