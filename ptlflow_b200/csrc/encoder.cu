@@ -215,6 +215,116 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x
   }
 }
 
+// ---- instance norm, one kernel, one HBM read ------------------------------------------------------------------
+// Statistics and normalisation of the SAME image back to back, so the second read of the image comes from L2: the grid is
+// `ipw` images x `G` CTAs (one wave of the machine, all co-resident); the G CTAs of an image reduce their pixel slices,
+// meet at a per-image counter in global memory, then normalise their slices.  `ipw` is chosen so that the images of a wave
+// (input + output) fit the L2.  The two-kernel form reads every activation tensor twice from HBM (16 frames x 220 x 512 x
+// 64 channels = 230 MB per layer-1 tensor, twice the 126 MB L2): 0.48 ms of statistics passes per step (bench r02c).
+template <typename T>
+__global__ void __launch_bounds__(256) inorm_fused_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                                                          double* __restrict__ stats, unsigned* __restrict__ counters, int B, int HW, int C,
+                                                          float eps, int relu, int G, int ipw) {
+  extern __shared__ float acc[];  // [2][C] partial sums, then [2][C] scale / shift
+  const int iw = blockIdx.x / G, g = blockIdx.x - iw * G;
+  const int c8n = C / 8;
+  const int lanes = blockDim.x / c8n;
+  const int co = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+  const int slice = (HW + G - 1) / G;
+  const int p0 = g * slice, p1 = min(p0 + slice, HW);
+  const bool pow2 = (c8n & (c8n - 1)) == 0 && c8n <= 32 && (blockDim.x % c8n) == 0;
+  for (int b = iw; b < B; b += ipw) {
+    // ---- phase 1: sums of this CTA's slice ----
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const size_t base = (size_t)b * HW * C + 8 * co;
+    float s[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+    if (pl < lanes) {
+#pragma unroll 4
+      for (int p = p0 + pl; p < p1; p += lanes) {
+        float v[8];
+        load8<T>(x + base + (size_t)p * C, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s[k] += v[k];
+          q[k] = fmaf(v[k], v[k], q[k]);
+        }
+      }
+    }
+    if (pow2) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        for (int o = c8n; o < 32; o <<= 1) {
+          s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+          q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+        }
+      }
+    }
+    if (pl < lanes && (!pow2 || (threadIdx.x & 31) < c8n)) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&acc[8 * co + k], s[k]);
+        atomicAdd(&acc[C + 8 * co + k], q[k]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      const int c = i % C, which = i / C;
+      atomicAdd(stats + ((size_t)b * C + c) * 2 + which, (double)acc[i]);
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- meet the other CTAs of this image ----
+    if (threadIdx.x == 0) {
+      atomicAdd(counters + b, 1u);
+      const unsigned long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned*>(counters + b) < (unsigned)G) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000ull) __trap();  // ~2 s: a scheduling assumption failed -- an error, never a hang
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    // ---- phase 2: scale / shift of the image, then this CTA's slice again (L2) ----
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double sum = __ldcg(stats + ((size_t)b * C + c) * 2), sq = __ldcg(stats + ((size_t)b * C + c) * 2 + 1);
+      const double mean = sum / HW;
+      double var = sq / HW - mean * mean;
+      var = var < 0 ? 0 : var;
+      const float rstd = rsqrtf((float)var + eps);
+      acc[c] = rstd;
+      acc[C + c] = (float)(-mean) * rstd;
+    }
+    __syncthreads();
+    if (pl < lanes) {
+      float sc[8], sh[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sc[k] = acc[8 * co + k];
+        sh[k] = acc[C + 8 * co + k];
+      }
+#pragma unroll 4
+      for (int p = p0 + pl; p < p1; p += lanes) {
+        const size_t off = base + (size_t)p * C;
+        float v[8], r[8];
+        load8<T>(x + off, v);
+        if (residual) load8<T>(residual + off, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float o = fmaf(v[k], sc[k], sh[k]);
+          if (relu) o = fmaxf(o, 0.f);
+          if (residual) o = fmaxf(r[k] + o, 0.f);
+          v[k] = o;
+        }
+        store8<T>(y + off, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace pfb
 
 using namespace pfb;
@@ -267,8 +377,29 @@ extern "C" PFB_API int pfb_instance_norm_act(const void* x, void* y, const void*
   cudaStream_t s = as_stream(stream);
   const int HW = H * W;
   double* stats = reinterpret_cast<double*>(workspace);
-  PFB_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(double), s));
+  // sums, and (fused kernel) one arrival counter per image right behind them: the scale / shift area of the workspace
+  PFB_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * C * 2 * sizeof(double) + (size_t)B * sizeof(unsigned), s));
   PFB_CHECK_ARG(B <= 65535, "instance_norm_act: batch too large");
+  {
+    static const int env_fused = getenv("PFB_INORM_FUSED") ? atoi(getenv("PFB_INORM_FUSED")) : 1;
+    const size_t image_bytes = (size_t)HW * C * dtype_size(dtype);
+    if (env_fused && dtype != PFB_F32 && C <= 256 && (256 % (C / 8) == 0 || C / 8 <= 32) && HW >= 1024) {
+      // images per wave: input + output (+ residual) of a wave within ~half of the 126 MB L2; at least 2 CTAs per image
+      const size_t per_image = image_bytes * (residual ? 3 : 2);
+      int ipw = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (size_t)(60u << 20) / std::max<size_t>(per_image, 1)));
+      const int sms = sm_count();
+      if (ipw > sms / 2) ipw = sms / 2;
+      const int G = std::max(1, sms / ipw);
+      unsigned* counters = reinterpret_cast<unsigned*>(stats + (size_t)B * C * 2);
+      ProfScope prof(KC_ENC_AFFINE, s);
+      PFB_DISPATCH_DTYPE(dtype, T, {
+        inorm_fused_kernel<T><<<ipw * G, 256, 2 * C * sizeof(float), s>>>((const T*)x, (const T*)residual, (T*)y, stats, counters, B, HW, C, eps,
+                                                                        relu, G, ipw);
+      });
+      PFB_LAUNCH_CHECK();
+      return PFB_OK;
+    }
+  }
   // plenty of blocks, few global atomics (fewer, fatter blocks were measured slower: r01 launch list v19)
   const int threads = 256;
   static const int env_ppb = getenv("PFB_STATS_PPB") ? atoi(getenv("PFB_STATS_PPB")) : 0;  // tuning knob

@@ -1,10 +1,12 @@
 set -x
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_umma.py tests/test_gpu_e2e.py tests/test_gpu_configs.py -m gpu -q -p no:cacheprovider 2>&1 | tail -30 ) > gpurun_out/pytest_r02e.log 2>&1
+( time timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -30 ) > gpurun_out/pytest_r02e.log 2>&1
 tail -8 gpurun_out/pytest_r02e.log
 Q="--no-comparators --no-cpu-baseline --no-parity --protocol-samples 0 --sustained-seconds 0"
 timeout 600 python bench.py $Q > gpurun_out/bench_r02e.json 2> gpurun_out/bench_r02e.log
 PFB_CONV_TMA_STORE=0 timeout 300 python bench.py $Q > gpurun_out/bench_r02e_notmastore.json 2> gpurun_out/bench_r02e_notmastore.log
+PFB_INORM_FUSED=0 timeout 300 python bench.py $Q > gpurun_out/bench_r02e_noinormfused.json 2> gpurun_out/bench_r02e_noinormfused.log
+timeout 300 python bench.py --inflight 2 $Q > gpurun_out/bench_r02e_inflight2.json 2> gpurun_out/bench_r02e_inflight2.log
 rm -f gpurun_out/conv_trace_e.jsonl
 PFB_CONV_TRACE=gpurun_out/conv_trace_e.jsonl PFB_CUDA_GRAPH=0 timeout 300 python tools/profile_step.py --iters 1 --warmup 1 > gpurun_out/trace_e.log 2>&1
 python tools/conv_trace_report.py gpurun_out/conv_trace_e.jsonl 1.9 > gpurun_out/conv_trace_e.txt 2>&1
