@@ -157,7 +157,9 @@ __device__ __forceinline__ void issue_taps(uint32_t d, uint32_t a_lo, uint32_t a
 // EPI (the pfb_epilogue) is a template parameter: with a run-time switch the register allocation of every epilogue was the
 // union of all of them (h, z, addend and bias operands live together), and the staged-store version spilled.
 template <typename T, int CG, int EPI>
-__global__ void __maxnreg__(192)  // 10 warps x 192 registers (allocated per warp in units of 512: 200 does not launch); ptxas stops at 168 under __launch_bounds__(320, 1)
+// 10 warps = 3 + 3 + 2 + 2 per SM sub-partition, each with 16 K registers: 168 registers per thread is the hardware ceiling
+// (ptxas picks it under __launch_bounds__(320, 1); __maxnreg__(192 / 200) compiles but does not launch).
+__global__ void __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const ConvUmmaArgs a) {
@@ -426,8 +428,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       const uint32_t taddr = tmem_base + t * a.acc_stride + ((uint32_t)(quarter * 32) << 16);
       // TMEM reads are software-pipelined too: the load of chunk c + 64 is issued as soon as chunk c has been moved
       // to v[], and completes under the arithmetic and the stores of chunk c.
+      // (the gate epilogues hold h / z / addend operands as well: their accumulator chunk is fetched at the top of its own
+      //  iteration instead of one ahead, which keeps them inside the 168-register ceiling)
+      constexpr bool kTmemAhead = EPI != PFB_EPI_GRU_ZR && EPI != PFB_EPI_GRU_Q && EPI != PFB_EPI_AXPY;
       uint32_t r[32];
-      if (group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
+      if (kTmemAhead && group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
       // 32 packed values -> this thread's half (group) of its pixel's 128-byte row in the staging buffer
       auto stage32 = [&](const uint4 (&pk)[4]) {
         uint8_t* sb = smemO + row * 128;
@@ -471,7 +476,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           }
         }
         if (c + 64 < a.NT) {  // warp-uniform
-          tmem_ld_32x32(taddr + c + 64, r);
+          if (kTmemAhead) tmem_ld_32x32(taddr + c + 64, r);
           if (aux_h_any) issue_h(c + 64, hnext);
           if (kAddAhead) issue_add(c + 64, anext);
         }
