@@ -417,10 +417,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       uint4 hnext[4], anext[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) hnext[q] = anext[q] = make_uint4(0u, 0u, 0u, 0u);
-      if (aux_h_any) issue_h(group * 32, hnext);
-      // (the q epilogue carries h one chunk ahead; its z and addend are requested at the top of their own chunk instead,
-      //  which keeps the kernel inside the 192-register budget)
+      // (the q epilogue needs h, z and the addend: it requests all three at the top of their own chunk -- two chunks per tile --
+      //  instead of one chunk ahead, which keeps it inside the 168-register ceiling without spills)
       constexpr bool kAddAhead = EPI != PFB_EPI_GRU_Q;
+      if (aux_h_any && kAddAhead) issue_h(group * 32, hnext);
       if (kAddAhead) issue_add(group * 32, anext);
       mbar_wait(&bars->acc_full[t], tuse & 1);
       tc_fence_after();
@@ -445,10 +445,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
        if (c < a.NT) {
         float v[32];  // (the last block of an NT % 64 == 32 tile has no chunk for group 1, which still joins the barriers below)
         const int n = n0 + c;  // first output channel of this chunk
+        if (!kTmemAhead) tmem_ld_32x32(taddr + c, r);
         uint4 hraw[4], zraw[4];
         issue_z(c, zraw);
+        if (!kAddAhead) issue_h(c, hraw);
+        else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) hraw[q] = hnext[q];
+          for (int q = 0; q < 4; ++q) hraw[q] = hnext[q];
+        }
         if (addp) {  // warp-uniform: per-pixel addend instead of the per-channel bias
           if (!kAddAhead) issue_add(c, anext);
           uint4 araw[4];
@@ -477,7 +481,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         }
         if (c + 64 < a.NT) {  // warp-uniform
           if (kTmemAhead) tmem_ld_32x32(taddr + c + 64, r);
-          if (aux_h_any) issue_h(c + 64, hnext);
+          if (aux_h_any && kAddAhead) issue_h(c + 64, hnext);
           if (kAddAhead) issue_add(c + 64, anext);
         }
         if (ok || a.tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)

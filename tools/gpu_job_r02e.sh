@@ -5,7 +5,7 @@ tail -8 gpurun_out/pytest_r02e.log
 Q="--no-comparators --no-cpu-baseline --no-parity --protocol-samples 0 --sustained-seconds 0"
 timeout 600 python bench.py $Q > gpurun_out/bench_r02e.json 2> gpurun_out/bench_r02e.log
 PFB_CONV_TMA_STORE=0 timeout 300 python bench.py $Q > gpurun_out/bench_r02e_notmastore.json 2> gpurun_out/bench_r02e_notmastore.log
-PFB_INORM_FUSED=0 timeout 300 python bench.py $Q > gpurun_out/bench_r02e_noinormfused.json 2> gpurun_out/bench_r02e_noinormfused.log
+PFB_INORM_FUSED=1 timeout 300 python bench.py $Q > gpurun_out/bench_r02e_inormfused.json 2> gpurun_out/bench_r02e_inormfused.log
 timeout 300 python bench.py --inflight 2 $Q > gpurun_out/bench_r02e_inflight2.json 2> gpurun_out/bench_r02e_inflight2.log
 rm -f gpurun_out/conv_trace_e.jsonl
 PFB_CONV_TRACE=gpurun_out/conv_trace_e.jsonl PFB_CUDA_GRAPH=0 timeout 300 python tools/profile_step.py --iters 1 --warmup 1 > gpurun_out/trace_e.log 2>&1
