@@ -414,25 +414,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           for (int q = 0; q < 4; ++q) aq[q] = reinterpret_cast<const uint4*>(addp + c)[q];
         }
       };
-      uint4 hnext[4], anext[4];
+      uint4 hnext[4], znext[4], anext[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) hnext[q] = anext[q] = make_uint4(0u, 0u, 0u, 0u);
-      // (the q epilogue needs h, z and the addend: it requests all three at the top of their own chunk -- two chunks per tile --
-      //  instead of one chunk ahead, which keeps it inside the 168-register ceiling without spills)
-      constexpr bool kAddAhead = EPI != PFB_EPI_GRU_Q;
-      if (aux_h_any && kAddAhead) issue_h(group * 32, hnext);
-      if (kAddAhead) issue_add(group * 32, anext);
+      for (int q = 0; q < 4; ++q) hnext[q] = znext[q] = anext[q] = make_uint4(0u, 0u, 0u, 0u);
+      // Operand prefetch.  Plain epilogues: the next chunk's accumulator / residual is requested as soon as the current chunk
+      // has been moved out of r[] ("early").  Gate epilogues (z|r, q, axpy) also hold h / z / addend: they request the next
+      // chunk's operands only AFTER the current chunk has been packed ("late"), when its registers are dead -- the loads then
+      // fly under the staging barriers and the TMA issue.  That keeps every instantiation inside the 168-register ceiling
+      // without spills and without exposing the L2 latency per chunk (in-place loads cost +2..6 us per gate launch, r02e).
+      constexpr bool kLate = EPI == PFB_EPI_GRU_ZR || EPI == PFB_EPI_GRU_Q || EPI == PFB_EPI_AXPY;
+      if (aux_h_any) issue_h(group * 32, hnext);
+      issue_z(group * 32, znext);
+      issue_add(group * 32, anext);
       mbar_wait(&bars->acc_full[t], tuse & 1);
       tc_fence_after();
       if (warp == 0 && i < 3) PFB_TR(12 + i);
       const uint32_t taddr = tmem_base + t * a.acc_stride + ((uint32_t)(quarter * 32) << 16);
       // TMEM reads are software-pipelined too: the load of chunk c + 64 is issued as soon as chunk c has been moved
       // to v[], and completes under the arithmetic and the stores of chunk c.
-      // (the gate epilogues hold h / z / addend operands as well: their accumulator chunk is fetched at the top of its own
-      //  iteration instead of one ahead, which keeps them inside the 168-register ceiling)
-      constexpr bool kTmemAhead = EPI != PFB_EPI_GRU_ZR && EPI != PFB_EPI_GRU_Q && EPI != PFB_EPI_AXPY;
       uint32_t r[32];
-      if (kTmemAhead && group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
+      if (group * 32 < a.NT) tmem_ld_32x32(taddr + group * 32, r);
       // 32 packed values -> this thread's half (group) of its pixel's 128-byte row in the staging buffer
       auto stage32 = [&](const uint4 (&pk)[4]) {
         uint8_t* sb = smemO + row * 128;
@@ -445,16 +446,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
        if (c < a.NT) {
         float v[32];  // (the last block of an NT % 64 == 32 tile has no chunk for group 1, which still joins the barriers below)
         const int n = n0 + c;  // first output channel of this chunk
-        if (!kTmemAhead) tmem_ld_32x32(taddr + c, r);
         uint4 hraw[4], zraw[4];
-        issue_z(c, zraw);
-        if (!kAddAhead) issue_h(c, hraw);
-        else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) hraw[q] = hnext[q];
-        }
+        for (int q = 0; q < 4; ++q) { hraw[q] = hnext[q]; zraw[q] = znext[q]; }
         if (addp) {  // warp-uniform: per-pixel addend instead of the per-channel bias
-          if (!kAddAhead) issue_add(c, anext);
           uint4 araw[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) araw[q] = anext[q];
@@ -479,10 +474,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb[q].w;
           }
         }
-        if (c + 64 < a.NT) {  // warp-uniform
-          if (kTmemAhead) tmem_ld_32x32(taddr + c + 64, r);
-          if (aux_h_any && kAddAhead) issue_h(c + 64, hnext);
-          if (kAddAhead) issue_add(c + 64, anext);
+        if (!kLate && c + 64 < a.NT) {  // warp-uniform
+          tmem_ld_32x32(taddr + c + 64, r);
+          if (aux_h_any) issue_h(c + 64, hnext);
+          issue_add(c + 64, anext);
         }
         if (ok || a.tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)
         T* out = reinterpret_cast<T*>(a.out);
@@ -583,6 +578,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             pk[q].z = pack2<T>(v[8 * q + 4], v[8 * q + 5]);
             pk[q].w = pack2<T>(v[8 * q + 6], v[8 * q + 7]);
           }
+        }
+        if (kLate && c + 64 < a.NT) {  // warp-uniform
+          tmem_ld_32x32(taddr + c + 64, r);
+          if (aux_h_any) issue_h(c + 64, hnext);
+          issue_z(c + 64, znext);
+          issue_add(c + 64, anext);
         }
        }
        if (a.tma_out) {
