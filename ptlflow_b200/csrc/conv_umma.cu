@@ -164,6 +164,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, const ConvUmmaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // only the plain epilogues stage their outputs (compile-time: the gate instantiations carry none of the staging state)
+  constexpr bool kPlain = EPI == PFB_EPI_LINEAR || EPI == PFB_EPI_RELU || EPI == PFB_EPI_RELU_APPEND_FLOW;
+  const bool tma_out = kPlain && a.tma_out;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + a.a_stages * a.a_slot_bytes;
@@ -173,7 +176,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   // than the tile's MMAs once the GRU lost its context third.  Staged, the stores are conflict-free 16-byte shared-memory
   // writes and the global side is the TMA unit writing whole 128-byte rows.
   uint8_t* smemO = smemB + a.b_stages * a.b_slot_bytes;
-  float* sbias = reinterpret_cast<float*>(smemO + (a.tma_out ? kATileBytes : 0));  // n_tiles * NT <= kMaxBias floats
+  float* sbias = reinterpret_cast<float*>(smemO + (tma_out ? kATileBytes : 0));  // n_tiles * NT <= kMaxBias floats
   ConvBars* bars = reinterpret_cast<ConvBars*>(reinterpret_cast<uint8_t*>(sbias) + kMaxBias * sizeof(float));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,7 +216,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tm0);
     prefetch_tmap(&tmW);
-    if (a.tma_out) prefetch_tmap(&tmO0);
+    if (tma_out) prefetch_tmap(&tmO0);
   }
   tc_fence_before();
   __syncthreads();
@@ -422,7 +425,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       // chunk's operands only AFTER the current chunk has been packed ("late"), when its registers are dead -- the loads then
       // fly under the staging barriers and the TMA issue.  That keeps every instantiation inside the 168-register ceiling
       // without spills and without exposing the L2 latency per chunk (in-place loads cost +2..6 us per gate launch, r02e).
-      constexpr bool kLate = EPI == PFB_EPI_GRU_ZR || EPI == PFB_EPI_GRU_Q || EPI == PFB_EPI_AXPY;
+      // Measured (launch lists r02c / r02e / r02f): the staged stores win on the plain epilogues (convc1 27.7 -> 20.8 us, flow
+      // head 35.1 -> 29.4 us) but lose on the gate epilogues, whose warps are unevenly loaded (r half vs z half) and meet at two
+      // barriers per 64-column block: z|r 41.7 -> 45.0 us, q 40.0 -> 49.2 us.  The host therefore stages only plain epilogues
+      // (conv2d_umma: tma_out), and the gates keep direct stores with everything requested one chunk ahead.
+      constexpr bool kLate = false;
       if (aux_h_any) issue_h(group * 32, hnext);
       issue_z(group * 32, znext);
       issue_add(group * 32, anext);
@@ -479,19 +486,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           if (aux_h_any) issue_h(c + 64, hnext);
           issue_add(c + 64, anext);
         }
-        if (ok || a.tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)
+        if (ok || tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)
         T* out = reinterpret_cast<T*>(a.out);
         switch (EPI) {
           case PFB_EPI_LINEAR: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] *= a.scale;
-            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (!tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_RELU: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
-            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (!tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_LINEAR_F32: {  // fp32 output (16-byte aligned rows: out_stride % 4 == 0)
@@ -514,7 +521,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[8 * q + e] = h[e] + a.scale * v[8 * q + e];
             }
-            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
+            if (!tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, a.Cout - n);
             break;
           }
           case PFB_EPI_RELU_APPEND_FLOW: {
@@ -530,14 +537,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
               }
               valid += 2;
             }
-            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
+            if (!tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, valid);
             break;
           }
           case PFB_EPI_GRU_ZR: {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = __fdividef(1.f, 1.f + __expf(-v[e]));  // sigmoid: 2 MUFU ops
             if (n < hd) {
-              if (!a.tma_out) store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
+              if (!tma_out) store32<T>(reinterpret_cast<T*>(a.aux_z) + p * hd + n, v, 32);
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -546,7 +553,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[8 * q + e] *= h[e];
               }
-              if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
+              if (!tma_out) store32<T>(out + p * a.out_stride + a.out_offset + (n - hd), v, 32);
             }
             break;
           }
@@ -563,14 +570,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
                 v[8 * q + e] = (1.f - z[e]) * h[e] + z[e] * th;
               }
             }
-            if (!a.tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
+            if (!tma_out) store32<T>(out + p * a.out_stride + a.out_offset + n, v, 32);
             break;
           }
           default:
             break;
         }
         }
-        if (a.tma_out) {
+        if (tma_out) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             pk[q].x = pack2<T>(v[8 * q + 0], v[8 * q + 1]);
@@ -586,7 +593,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           issue_add(c + 64, anext);
         }
        }
-       if (a.tma_out) {
+       if (tma_out) {
          // One 64-column block, staged by both epilogue groups, leaves as one bulk store (single staging buffer: the previous
          // block's store has had this block's arithmetic to drain; thread 0 confirms it before anybody overwrites the buffer).
          if (threadIdx.x == 0) tma_store_wait_read();
@@ -612,7 +619,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       }
     }
   }
-  if (a.tma_out && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete (not only read)
+  if (tma_out && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete (not only read)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) PFB_TR(18);
@@ -788,8 +795,8 @@ int conv2d_umma(const pfb_conv_params* p, cudaStream_t s) {
   a.b_tap_bytes = (a.NT / CG) * 128;
   {
     static const int env_tma_out = getenv("PFB_CONV_TMA_STORE") ? atoi(getenv("PFB_CONV_TMA_STORE")) : 1;
-    a.tma_out = env_tma_out && p->epilogue != PFB_EPI_LINEAR_F32 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
-                (p->epilogue != PFB_EPI_GRU_ZR || (p->hidden % 64 == 0 && (reinterpret_cast<uintptr_t>(p->aux_z) & 15) == 0));
+    const bool plain = p->epilogue == PFB_EPI_LINEAR || p->epilogue == PFB_EPI_RELU || p->epilogue == PFB_EPI_RELU_APPEND_FLOW;
+    a.tma_out = env_tma_out && plain && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0;
   }
   const int ring_budget = (a.tma_out ? 192 : 208) * 1024;  // 16 KB of output staging + 4 KB of bias come out of the rings' share
   {
