@@ -484,6 +484,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         if (!kLate && c + 64 < a.NT) {  // warp-uniform
           tmem_ld_32x32(taddr + c + 64, r);
           if (aux_h_any) issue_h(c + 64, hnext);
+          issue_z(c + 64, znext);
           issue_add(c + 64, anext);
         }
         if (ok || tma_out) {  // (staged rows of out-of-image pixels are clipped by the TMA unit)
