@@ -236,7 +236,19 @@ def run_ours(args):
     assert world == max(1, args.gpus) or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    sharding.init_process_group("nccl")
+    # NCCL may print its version banner on stdout (NCCL_DEBUG=VERSION on some boxes); stdout carries exactly one JSON line,
+    # so file descriptor 1 points at stderr while the process group comes up and the first collective runs
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        sharding.init_process_group("nccl")
+        sharding.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     lib = _lib.load()
 
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
