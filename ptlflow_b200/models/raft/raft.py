@@ -99,6 +99,8 @@ class RAFT(BaseModel):
         # one CUDA graph per (input shape, dtype, iters, stream): PFB_CUDA_GRAPH=0 or model.use_cuda_graph = False -> eager launches
         self.use_cuda_graph = bool(int(_os.environ.get("PFB_CUDA_GRAPH", "1")))
         self._graphs: Dict[tuple, tuple] = {}
+        self._graph_seen: Dict[tuple, int] = {}
+        self.graph_capture_after = int(_os.environ.get("PFB_GRAPH_AFTER", "1"))  # eager calls of a (shape, ...) key before it is captured
         self._graph_sig = None
         self.graph_replays = 0
         self.graph_launches_replayed = 0  # this library's kernel launches replayed from graphs (bench.py: gpu_launches)
@@ -235,10 +237,20 @@ class RAFT(BaseModel):
         sig = self._weights_signature()
         if self._graph_sig != sig:
             self._graphs.clear()
+            self._graph_seen.clear()
             self._graph_sig = sig
         key = self._graph_key(images, flow_init)
         ent = self._graphs.get(key)
         dev = images.device
+        if ent is None and self.graph_capture_after > 0:
+            # a capture costs about four forwards (two warm-ups, the capture, its first replay) and pins the forward's memory:
+            # only shapes that come back are captured (infer.py / validate.py feed dataset-dependent sizes, often once each)
+            seen = self._graph_seen.get(key, 0)
+            if seen < self.graph_capture_after:
+                if len(self._graph_seen) > 64:
+                    self._graph_seen.clear()
+                self._graph_seen[key] = seen + 1
+                return self._forward_device(images, flow_init), False
         if ent is None:
             cur = torch.cuda.current_stream(dev)
             static_in = torch.empty_like(images)
@@ -274,7 +286,7 @@ class RAFT(BaseModel):
         graph.replay()
         self.graph_replays += 1
         self.graph_launches_replayed += launches
-        return flow_up, flow_small
+        return (flow_up, flow_small), True
 
     def forward(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Estimate optical flow between a pair of frames (eval semantics of raft.py:125-194)."""
@@ -293,7 +305,7 @@ class RAFT(BaseModel):
                 flow_init = forward_interpolate_batch(prev["flow_small"]).to(device=images.device, dtype=torch.float32).contiguous()
             use_graph = self.use_cuda_graph and not torch.cuda.is_current_stream_capturing()
             if use_graph:
-                flow_up, flow_small = self._forward_graphed(images, flow_init)
+                (flow_up, flow_small), use_graph = self._forward_graphed(images, flow_init)  # (False: ran eagerly, fresh tensors)
             else:
                 flow_up, flow_small = self._forward_device(images, flow_init)
             out_dtype = inputs["images"].dtype

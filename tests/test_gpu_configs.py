@@ -103,10 +103,13 @@ def test_cuda_graph_matches_eager():
         model.use_cuda_graph = False
         e1, e2 = model({"images": img})["flows_fp32"].clone(), model({"images": img2})["flows_fp32"].clone()
         model.use_cuda_graph = True
-        g1 = model({"images": img})["flows_fp32"].clone()
+        g0 = model({"images": img})["flows_fp32"].clone()   # first sight of the shape: still eager (graph_capture_after = 1)
+        assert model.graph_replays == 0
+        g1 = model({"images": img})["flows_fp32"].clone()   # second: captured and replayed
         g2 = model({"images": img2})["flows_fp32"].clone()  # replay with different frames
         g1b = model({"images": img})["flows_fp32"].clone()
     assert model.graph_replays == 3 and model.graph_launches_replayed > 0
+    assert (g0 - e1).abs().max().item() < 5e-3
     # instance-norm statistics are summed with atomics: agreement up to fp32 summation order through 5 iterations
     assert (g1 - e1).abs().max().item() < 5e-3 and (g2 - e2).abs().max().item() < 5e-3
     assert (g1b - g1).abs().max().item() < 5e-3
