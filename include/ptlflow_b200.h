@@ -121,6 +121,17 @@ PFB_API int pfb_corr_lookup_onthefly(const void* fmap1, void* const* fmap2_pyram
                              int B, int H, int W, int C, int levels, int radius, pfb_dtype dtype,
                              pfb_dtype out_dtype, int out_nchw, int out_stride, pfb_stream stream);
 
+/* a4 on the tensor cores (f16 / bf16, radius 4, C % 64 == 0, C <= 256, pixel-major output): every 8 x 16 tile of neighbouring queries
+ * multiplies its query vectors with the region of fmap2_pyramid[l] that holds all its windows (tcgen05 GEMM, TMA-fed, out-of-map
+ * targets zero-filled by the TMA unit) and blends its windows out of the accumulator; queries whose window does not fit the region
+ * (rough flow inside a tile) are recomputed by the SIMT kernel of pfb_corr_lookup_onthefly, so the values never depend on the flow.
+ * workspace: pfb_corr_lookup_onthefly_tc_workspace_bytes(B, H, W) bytes (one flag per query).  Same output as
+ * pfb_corr_lookup_onthefly(..., out_nchw = 0) up to the storage-type rounding of the products. */
+PFB_API size_t pfb_corr_lookup_onthefly_tc_workspace_bytes(int B, int H, int W);
+PFB_API int pfb_corr_lookup_onthefly_tc(const void* fmap1, void* const* fmap2_pyramid, const float* coords, void* out, void* workspace,
+                                        int B, int H, int W, int C, int levels, int radius, pfb_dtype dtype, int out_stride,
+                                        pfb_stream stream);
+
 /* The reference plugin's own entry point, same tensor contract:
  *   alt_cuda_corr.forward(fmap1, fmap2, coords, radius) -> [corr]     correlation.cpp:23-33
  * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C], coords [B,1,H1,W1,2] fp32, out [B,1,(2r+1)^2,H1,W1];

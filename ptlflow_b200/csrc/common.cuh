@@ -130,6 +130,8 @@ int conv_flow7x7(const pfb_conv_params* p, cudaStream_t s);
 int corr_volume_umma(const void* f1, const void* f2, void* const* pyr, int B, int N1, int H, int W, int C, int L, float scale,
                      pfb_dtype dt, cudaStream_t s);
 bool corr_volume_umma_supported(int B, int H, int W, int C, int L, pfb_dtype dt);
+// corr_onthefly_umma.cu
+bool corr_onthefly_umma_supported(int B, int H, int W, int C, int levels, int radius, pfb_dtype dt, int out_stride);
 // corr_umma.cu, tiled pyramid (layout: corr_tiled.cu)
 int corr_volume_tiled(const void* f1, const void* f2, void* const* pyr, int B, int N1, int H, int W, int C, int L, float scale,
                       pfb_dtype dt, cudaStream_t s);

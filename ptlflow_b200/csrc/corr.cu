@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(128) corr_onthefly_kernel(const T* __restrict_
                                                             const float* __restrict__ coords,
                                                             TO* __restrict__ out, int nq, int hw, int C,
                                                             int levels, int r, float scale, int nchw,
-                                                            int out_stride) {
+                                                            int out_stride, const unsigned char* __restrict__ flags) {
   extern __shared__ float smem[];
   const int D = 2 * r + 2, K = 2 * r + 1;
   const int warps = blockDim.x >> 5;
@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(128) corr_onthefly_kernel(const T* __restrict_
   float* win = smem + warps * C + warp * D * D;     // window of raw dot products
   const int q = blockIdx.x * warps + warp;
   if (q >= nq) return;
+  if (flags && !flags[q]) return;  // second pass behind the tensor-core kernel: only the queries it could not serve
   const T* f1 = fmap1 + (size_t)q * C;
   for (int c = lane; c < C; c += 32) qv[c] = to_f32(f1[c]);
   __syncwarp();
@@ -370,6 +371,9 @@ int corr_volume_simt(const void* f1, const void* f2, void* const* pyr, int B, in
   });
   return PFB_OK;
 }
+
+int corr_onthefly_simt_flagged(const void* fmap1, void* const* pyr, const float* coords, void* out, const unsigned char* flags, int B, int H,
+                               int W, int C, int levels, int radius, pfb_dtype dtype, int out_stride, cudaStream_t s);
 
 }  // namespace pfb
 
@@ -479,7 +483,7 @@ extern "C" PFB_API int pfb_corr_lookup_ex(void* const* pyramid, const int* level
 template <typename T>
 static int launch_onthefly_t(const void* fmap1, const LevelTable& lv, const float* coords, void* out, int nq,
                              int hw, int C, int levels, int radius, float scale, pfb_dtype out_dtype, int nchw,
-                             int out_stride, cudaStream_t s) {
+                             int out_stride, cudaStream_t s, const unsigned char* flags = nullptr) {
   const int D = 2 * radius + 2;
   const int warps = 4;
   size_t smem = (size_t)warps * (C + D * D) * sizeof(float);
@@ -491,7 +495,7 @@ static int launch_onthefly_t(const void* fmap1, const LevelTable& lv, const floa
     if (smem > 48 * 1024)                                                                                   \
       PFB_CUDA(cudaFuncSetAttribute(corr_onthefly_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     corr_onthefly_kernel<T, TO><<<grid, warps * 32, smem, s>>>(f1, lv, coords, (TO*)out, nq, hw, C, levels,  \
-                                                               radius, scale, nchw, out_stride);            \
+                                                               radius, scale, nchw, out_stride, flags);     \
   } while (0)
   if (out_dtype == PFB_F32) PFB_OTF(float);
   else if (out_dtype == PFB_F16) PFB_OTF(__half);
@@ -541,3 +545,19 @@ extern "C" PFB_API int pfb_alt_corr_forward(const void* fmap1, const void* fmap2
   });
   return PFB_OK;
 }
+
+namespace pfb {
+int corr_onthefly_simt_flagged(const void* fmap1, void* const* pyr, const float* coords, void* out, const unsigned char* flags, int B, int H,
+                               int W, int C, int levels, int radius, pfb_dtype dtype, int out_stride, cudaStream_t s) {
+  LevelTable lv;
+  if (fill_levels(lv, pyr, H, W, levels) != 0) {
+    set_error("corr_onthefly (flagged pass): fmap2 level missing or empty");
+    return PFB_ERR_ARG;
+  }
+  const float scale = 1.0f / sqrtf((float)C);
+  PFB_DISPATCH_DTYPE(dtype, T, {
+    return launch_onthefly_t<T>(fmap1, lv, coords, out, B * H * W, H * W, C, levels, radius, scale, dtype, 0, out_stride, s, flags);
+  });
+  return PFB_OK;
+}
+}  // namespace pfb

@@ -26,6 +26,7 @@ struct Workspace {
   size_t off_corr, off_cor1, off_corflo, off_flo1, off_motion, off_z, off_rh, off_fh, off_mh, off_mask, off_flow;
   size_t off_taps;          // flow head conv2 per-tap products [P][32] fp32 (tensor-core path)
   size_t off_vbuf, off_vT;  // gma: to_v(motion) [P][128] and its per-sample transpose [B][128][n_pad]
+  size_t off_flags;         // on-the-fly tensor-core lookup: one flag per query (queries recomputed by the SIMT pass)
   size_t off_ctx[4];        // iteration-invariant context terms of the GRU gates: zr1 [P][2hd], q1 [P][hd], zr2, q2 (tensor path)
   int n_pad;
   size_t total;
@@ -65,6 +66,7 @@ static Workspace plan(const pfb_raft_cfg* c) {
   w.n_pad = (int)align_up((size_t)c->H * c->W, 64);
   w.off_vbuf = take(c->variant == 2 ? P * 128 * es : 0);
   w.off_vT = take(c->variant == 2 ? (size_t)c->B * 128 * w.n_pad * es : 0);
+  w.off_flags = take(c->alternate_corr ? P : 0);
   for (int i = 0; i < 4; ++i)
     w.off_ctx[i] = take((c->variant != 1 && c->dtype != PFB_F32) ? P * (size_t)((i & 1) ? c->hidden_dim : 2 * c->hidden_dim) * es : 0);
   w.total = off;
@@ -153,6 +155,12 @@ static int run_context_terms(const Ctx& x) {
 
 static int lookup(const Ctx& x) {
   const pfb_raft_cfg* c = x.c;
+  if (c->alternate_corr) {
+    static const int env_tc = getenv("PFB_ONTHEFLY_TC") ? atoi(getenv("PFB_ONTHEFLY_TC")) : 1;
+    if (env_tc && c->impl != 1 && corr_onthefly_umma_supported(c->B, c->H, c->W, c->feat_dim, c->corr_levels, c->corr_radius, c->dtype, x.ws.corr_stride))
+      return pfb_corr_lookup_onthefly_tc(x.b->fmap1, x.b->pyramid, x.b->coords, x.at(x.ws.off_corr), x.at(x.ws.off_flags), c->B, c->H, c->W,
+                                         c->feat_dim, c->corr_levels, c->corr_radius, c->dtype, x.ws.corr_stride, (pfb_stream)x.s);
+  }
   if (c->alternate_corr)
     return pfb_corr_lookup_onthefly(x.b->fmap1, x.b->pyramid, x.b->coords, x.at(x.ws.off_corr), c->B, c->H, c->W,
                                     c->feat_dim, c->corr_levels, c->corr_radius, c->dtype, c->dtype, 0,

@@ -191,6 +191,25 @@ def corr_lookup_onthefly(fmap1: torch.Tensor, fmap2_pyramid: Sequence[torch.Tens
     return out
 
 
+def corr_lookup_onthefly_tc(fmap1: torch.Tensor, fmap2_pyramid: Sequence[torch.Tensor], coords: torch.Tensor, radius: int = 4,
+                            out_stride: Optional[int] = None) -> torch.Tensor:
+    """a4 on the tensor cores: fmap1 [B,H,W,C] f16/bf16, fmap2 levels, coords fp32 [B,H,W,2] -> pixel-major [B,H,W,out_stride]."""
+    require_cuda(fmap1, "fmap1"); require_cuda(coords, "coords")
+    B, H, W, Cc = fmap1.shape
+    L = len(fmap2_pyramid)
+    planes = L * (2 * radius + 1) ** 2
+    stride = (planes + 7) // 8 * 8 if out_stride is None else out_stride
+    out = torch.empty((B, H, W, stride), dtype=fmap1.dtype, device=fmap1.device)
+    lib = load()
+    ws = torch.empty(max(1, lib.pfb_corr_lookup_onthefly_tc_workspace_bytes(B, H, W)), dtype=torch.uint8, device=fmap1.device)
+    with torch.cuda.device(fmap1.device):
+        check(lib.pfb_corr_lookup_onthefly_tc(fmap1.data_ptr(), ptr_array(fmap2_pyramid), coords.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                              B, H, W, Cc, L, radius, dtype_code(fmap1.dtype), stride, stream_ptr(fmap1.device)),
+              "corr_lookup_onthefly_tc")
+    out._pfb_flags = ws  # (tests read how many queries took the SIMT pass)
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # conv building block
 # ------------------------------------------------------------------------------------------

@@ -180,3 +180,47 @@ def test_tiled_lookup_pad_columns_are_masked():
         v[((ys >= hl) | (xs >= wl)).expand_as(v)] = 1000.0
     bb = ops.corr_lookup_tiled(pyr, coords, radius, (h, w))
     assert torch.equal(a, bb)
+
+
+# ------------------------------------------------------------------------------------------
+# a4 on the tensor cores
+# ------------------------------------------------------------------------------------------
+OTF_CASES = [
+    # b, c, h, w, levels, sigma (px of coordinate noise: small = smooth flow, large = rough -> SIMT pass), dtype, tol
+    (1, 256, 24, 48, 4, 0.7, torch.float16, 2e-2),
+    (2, 256, 27, 45, 4, 1.5, torch.float16, 2e-2),   # partial tiles on both axes, odd level sizes
+    (1, 128, 16, 32, 3, 12.0, torch.float16, 2e-2),  # rough flow: most queries are flagged and recomputed
+    (1, 256, 55, 128, 4, 2.0, torch.bfloat16, 1.5e-1),
+    (1, 64, 9, 17, 2, 1.0, torch.float16, 2e-2),     # C = 64: a single K chunk
+]
+
+
+@pytest.mark.parametrize("b,c,h,w,levels,sigma,dtype,tol", OTF_CASES)
+def test_onthefly_tensor_core(b, c, h, w, levels, sigma, dtype, tol):
+    from ptlflow_b200 import ops
+
+    f1 = torch.from_numpy(synth.synth_normal("otc/f1", (b, c, h, w), 31))
+    f2 = torch.from_numpy(synth.synth_normal("otc/f2", (b, c, h, w), 31))
+    smooth = torch.from_numpy(synth.synth_normal("otc/s", (b, 2, 1, 1), 31, scale=3.0))  # a common displacement per sample
+    coords = O.coords_grid(b, h, w) + smooth + torch.from_numpy(synth.synth_normal("otc/c", (b, 2, h, w), 31, scale=sigma))
+    coords[0, :, 0, 0] = torch.tensor([-60.0, -60.0])                 # far out of bounds: zero window
+    coords[0, :, 0, 1] = torch.tensor([float(w) + 2.5, float(h) - 1.25])  # straddles the right / bottom border
+    coords[0, :, 1, 0] = torch.tensor([float("nan"), 0.0])            # non-finite: zero window like the SIMT kernel
+    pm = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)  # noqa: E731
+    cpm = coords.permute(0, 2, 3, 1).contiguous().to(DEV)
+    pyr = ops.feature_pyramid(pm(f2), levels)
+    out = ops.corr_lookup_onthefly_tc(pm(f1), pyr, cpm, 4)
+    planes = levels * 81
+    simt = ops.corr_lookup_onthefly(pm(f1), pyr, cpm, 4, nchw=False, out_stride=out.shape[-1])
+    flagged = int(out._pfb_flags.sum().item())
+    d = (out[..., :planes].float() - simt[..., :planes].float()).abs().max().item()
+    scale = max(1.0, simt[..., :planes].float().abs().max().item())
+    assert d < tol * scale, f"tensor-core vs SIMT on-the-fly: {d} (flagged {flagged} of {b * h * w})"
+    assert out[..., planes:].abs().max().item() == 0
+    if sigma < 3:
+        assert flagged < 0.2 * b * h * w, f"smooth flow but {flagged} of {b * h * w} queries left the tile regions"
+    # and against the oracle (features rounded to the storage type first, as the operator's contract says)
+    coords_ref = torch.nan_to_num(coords, nan=-1e6)
+    ref = O.alt_corr_lookup(f1.to(dtype).float(), f2.to(dtype).float(), coords_ref, 4, levels)
+    got = out[..., :planes].permute(0, 3, 1, 2).float().cpu()
+    assert (got - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
