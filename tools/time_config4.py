@@ -40,6 +40,17 @@ for name, dt in (("ours_onthefly_fp32", torch.float32), ("ours_onthefly_f16", to
     a, b = f1.to(dt), f2.to(dt)
     pyr = ops.feature_pyramid(b, L)
     out[name] = round(timeit(lambda: ops.corr_lookup_onthefly(a, pyr, coords, R, nchw=False)), 4)
+a16, b16 = f1.half(), f2.half()
+pyr16 = ops.feature_pyramid(b16, L)
+out["ours_onthefly_tensor_core_f16"] = round(timeit(lambda: ops.corr_lookup_onthefly_tc(a16, pyr16, coords, R)), 4)
+o_tc = ops.corr_lookup_onthefly_tc(a16, pyr16, coords, R)
+o_simt = ops.corr_lookup_onthefly(a16, pyr16, coords, R, nchw=False, out_stride=o_tc.shape[-1])
+out["tensor_core_vs_simt_max_abs"] = float((o_tc[..., :L * 81].float() - o_simt[..., :L * 81].float()).abs().max())
+out["tensor_core_flagged_queries"] = int(o_tc._pfb_flags.sum())
+for sig in (1.0, 8.0):  # the same with smoother / rougher coordinates (the region GEMM serves fewer queries when the flow is rough)
+    cs = (torch.stack([xs, ys], -1)[None] + sig * torch.randn(B, H, W, 2, device=dev)).contiguous()
+    o = ops.corr_lookup_onthefly_tc(a16, pyr16, cs, R)
+    out[f"ours_onthefly_tensor_core_f16_sigma{sig:g}"] = {"ms": round(timeit(lambda: ops.corr_lookup_onthefly_tc(a16, pyr16, cs, R)), 4), "flagged": int(o._pfb_flags.sum())}
 ref = build_ref.load()
 if ref is not None:
     pyr32 = ops.feature_pyramid(f2, L)
@@ -51,7 +62,6 @@ if ref is not None:
     ours = ops.corr_lookup_onthefly(f1, pyr32, coords, R, nchw=True) * (C ** 0.5)
     refv = torch.cat([o[:, 0] for o in ref_all()], dim=1)
     out["max_abs_diff_vs_reference_kernel"] = float((ours - refv).abs().max())
-a16, b16 = f1.half(), f2.half()
 t_build = timeit(lambda: ops.corr_volume_build_tiled(a16, b16, L), 5)
 pyr_t = ops.corr_volume_build_tiled(a16, b16, L)
 out["ours_materialised_f16"] = {"volume_build_once_ms": round(t_build, 4), "lookup_ms": round(timeit(lambda: ops.corr_lookup_tiled(pyr_t, coords, R, (H, W))), 4),
