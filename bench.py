@@ -79,6 +79,7 @@ def parse_args():
     ap.add_argument("--fp32-context", action="store_true", help="accuracy mode: context encoder in fp32 (RAFT.enable_fp32_context)")
     ap.add_argument("--protocol-samples", type=int, default=12, help="synchronised single forwards for the model_benchmark.py protocol (0 = skip)")
     ap.add_argument("--sustained-seconds", type=float, default=5.0, help="length of the sustained loop (0 = skip)")
+    ap.add_argument("--alternate-corr", action="store_true", help="on-the-fly correlation (no 4D volume), BASELINE config 4")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-comparators", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -253,7 +254,10 @@ def run_ours(args):
 
     dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
     torch.manual_seed(1234)
-    model = pb.get_model(args.model, args=Namespace(model=Namespace(iters=args.iters)))
+    mkw = dict(iters=args.iters)
+    if args.alternate_corr:
+        mkw["alternate_corr"] = True
+    model = pb.get_model(args.model, args=Namespace(model=Namespace(**mkw)))
     sd_fp32 = {k: v.detach().clone() for k, v in model.state_dict().items()}  # the fp32 weights the reference would hold
     if args.fp32_context:
         model.enable_fp32_context()
@@ -538,7 +542,7 @@ def run_ours(args):
         "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " storage, f32 accumulate/coordinates",
         "data": "synthetic (torch.rand frames, random-init weights, seed 1234)",
         "config": {"workload": f"{args.model} {W}x{H} {args.iters} iters, batch {B} per GPU (BASELINE.json configs[1])",
-                   "pairs_per_step_per_gpu": B, "batches_in_flight_per_gpu": args.inflight, "cuda_graph": bool(model.use_cuda_graph),
+                   "pairs_per_step_per_gpu": B, "batches_in_flight_per_gpu": args.inflight, "cuda_graph": bool(model.use_cuda_graph), "alternate_corr": bool(args.alternate_corr),
                    "fp32_context": bool(args.fp32_context), "value_remeasured": value_remeasured, "e2e_remeasured": e2e_remeasured,
                    "parallelism": f"replicas x{world}, frame pairs sharded, no data-path collective",
                    "l2": "per-step working set (>= 1 GB correlation pyramid at batch 8) exceeds the 126 MB L2; inputs rotate over a pool of 3 batches",

@@ -26,12 +26,16 @@ ap.add_argument("--iters", type=int, default=12)
 ap.add_argument("--dtype", default="fp16")
 ap.add_argument("--kernel-impl", type=int, default=0)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--alternate-corr", action="store_true")
 ap.add_argument("--cuda-graph", type=int, default=0, help="0 (default): eager launches, so every kernel shows up by name under ncu")
 a = ap.parse_args()
 
 dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[a.dtype]
 torch.manual_seed(1234)
-model = pb.get_model(a.model, args=Namespace(model=Namespace(iters=a.iters))).eval().cuda().to(dtype)
+mkw = dict(iters=a.iters)
+if a.alternate_corr:
+    mkw["alternate_corr"] = True
+model = pb.get_model(a.model, args=Namespace(model=Namespace(**mkw))).eval().cuda().to(dtype)
 model.kernel_impl = a.kernel_impl
 model.use_cuda_graph = bool(a.cuda_graph)
 x = torch.rand(a.batch, 2, 3, a.height, a.width, device="cuda", dtype=dtype)
