@@ -28,6 +28,7 @@ constexpr int kOtfTileBytes = 128 * 128;       // 128 rows x 64 channels
 constexpr int kOtfBandRows = 256;              // targets per band: 8 rows x 32 columns
 constexpr int kOtfMaxBands = 8;                // 7 * 8 + 1 = 57 region rows at most
 constexpr int kOtfRW = 32;
+constexpr int kOtfDumpPitch = 528;             // bytes per accumulator-dump row (256 targets x 2 bytes + 16)
 
 struct OtfArgs {
   const float* coords;
@@ -83,7 +84,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                       // kchunks x 16 KB
   uint8_t* sB = sA + a.kchunks * kOtfTileBytes;             // kchunks x 32 KB (>= 64 KB); after the MMAs: the accumulator dump [128][256]
-  const int b_bytes = a.kchunks * 2 * kOtfTileBytes < 4 * kOtfTileBytes ? 4 * kOtfTileBytes : a.kchunks * 2 * kOtfTileBytes;
+  const int b_bytes = a.kchunks * 2 * kOtfTileBytes < 128 * kOtfDumpPitch ? 5 * kOtfTileBytes : a.kchunks * 2 * kOtfTileBytes;
   unsigned short* sOut = reinterpret_cast<unsigned short*>(sB + b_bytes);  // [128][SP] staged outputs of one level
   OtfBars* bars = reinterpret_cast<OtfBars*>(reinterpret_cast<uint8_t*>(sOut) + ((128 * SP * 2 + 15) & ~15));
 
@@ -106,9 +107,12 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int q_local = threadIdx.x;  // epilogue threads: 0..127 = (row in tile) * 16 + (column in tile)
   uint32_t par_a = 0, par_b = 0, par_acc = 0;
 
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  // work item = (query tile, level): 4x more, 4x shorter items than whole tiles -- 255 tiles on 148 SMs are 2 rounds with the
+  // second one 72 % full, 1020 items are 6.9 rounds
+  for (int item = blockIdx.x; item < a.n_tiles * a.levels; item += gridDim.x) {
+    const int tile = item / a.levels, l = item - tile * a.levels;
     const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
-    __syncthreads();  // the previous tile's MMAs and gathers are done: sA / sB may be overwritten
+    __syncthreads();  // the previous item's MMAs and gathers are done: sA / sB may be overwritten
     if (warp == 4 && lane == 0) {
       mbar_arrive_expect_tx(&bars->a_full, a.kchunks * kOtfTileBytes);
       for (int k = 0; k < a.kchunks; ++k) tma_load_4d(sA + k * kOtfTileBytes, &tmA, &bars->a_full, k * 64, tx * 16, ty * 8, b);
@@ -124,7 +128,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       cy = c.y;
     }
     bool a_waited = false;
-    for (int l = 0; l < a.levels; ++l) {
+    {
       const CUtensorMap* tmB = l == 0 ? &tmB0 : (l == 1 ? &tmB1 : (l == 2 ? &tmB2 : &tmB3));
       const int Hl = a.lh[l], Wl = a.lw[l];
       // ---- window geometry of this query at this level ----
@@ -217,7 +221,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           // ---- epilogue: accumulator row -> shared memory (scaled by the blend weights later; storage-type rounding) ----
           mbar_wait(&bars->acc_full, par_acc);
           tc_fence_after();
-          uint8_t* drow = sB + q_local * 512;
+          uint8_t* drow = sB + q_local * kOtfDumpPitch;  // 528-byte rows: the 32 lanes' 16-byte stores fall on 32 different bank groups
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
@@ -231,9 +235,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
               u.y = otf_pack2<T>(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
               u.z = otf_pack2<T>(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
               u.w = otf_pack2<T>(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-              // 16-byte chunk (4c + g) of this thread's 512-byte row, XOR-swizzled by the row so that the 32 lanes of a warp
-              // (32 different rows, same chunk) hit 32 different bank groups
-              *reinterpret_cast<uint4*>(drow + ((((c << 2) | g) ^ (q_local & 31)) << 4)) = u;
+              *reinterpret_cast<uint4*>(drow + (((c << 2) | g) << 4)) = u;
             }
           }
           tc_fence_before();
@@ -248,8 +250,8 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
               for (int i = 0; i < D; ++i) {
                 const int e0 = rr * kOtfRW + cxo + i, e1 = e0 + kOtfRW;
-                up[i] = otf_bits_to_f32<T>(dr[((((e0 >> 3) ^ (q_local & 31)) << 3) | (e0 & 7))]);
-                dn[i] = otf_bits_to_f32<T>(dr[((((e1 >> 3) ^ (q_local & 31)) << 3) | (e1 & 7))]);
+                up[i] = otf_bits_to_f32<T>(dr[e0]);
+                dn[i] = otf_bits_to_f32<T>(dr[e1]);
               }
 #pragma unroll
               for (int i = 0; i < K; ++i)
@@ -282,7 +284,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       par_a ^= 1;
     } else par_a ^= 1;
     // pad columns of the pixel-major rows (out_stride > levels * 81): zero
-    if (warp < 4 && q_in) {
+    if (warp < 4 && q_in && l == 0) {
       unsigned short* dst = reinterpret_cast<unsigned short*>(a.out) + q * a.out_stride;
       for (int c = a.levels * KK; c < a.out_stride; ++c) dst[c] = 0;
     }
@@ -330,7 +332,7 @@ int corr_onthefly_umma(const void* fmap1, void* const* pyr, const float* coords,
     if (rc) return rc;
   }
   PFB_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * H * W, s));
-  const int b_bytes = std::max(a.kchunks * 2 * kOtfTileBytes, 4 * kOtfTileBytes);
+  const int b_bytes = a.kchunks * 2 * kOtfTileBytes < 128 * kOtfDumpPitch ? 5 * kOtfTileBytes : a.kchunks * 2 * kOtfTileBytes;
   const size_t smem = (size_t)a.kchunks * kOtfTileBytes + b_bytes + ((128 * 82 * 2 + 15) & ~15) + sizeof(OtfBars) + 1024;
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
