@@ -56,6 +56,11 @@ PFB_API int pfb_version(void);
 PFB_API const char* pfb_last_error(void);
 /* sm major*10+minor of the current device, or negative status. */
 PFB_API int pfb_device_arch(void);
+/* A stream of the current device that belongs to the caller alone (cudaStreamNonBlocking).  The host side captures its CUDA
+ * graphs on one: a stream handed out by a framework's stream pool can be the same underlying stream as one another host
+ * thread is launching on, and that thread's work would land in the capture. */
+PFB_API int pfb_stream_create(pfb_stream* out);
+PFB_API int pfb_stream_destroy(pfb_stream stream);
 
 /* ------------------------------------------------------------------------------------
  * a1 + a2: all-pairs correlation volume and its pooled pyramid

@@ -7,6 +7,7 @@ PyTorch fallback for the hot path.  Build it with ``python -m ptlflow_b200.csrc.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import os
 from typing import Optional
 
@@ -86,6 +87,8 @@ SIGNATURES = {
     "pfb_version": (_I, []),
     "pfb_last_error": (C.c_char_p, []),
     "pfb_device_arch": (_I, []),
+    "pfb_stream_create": (_I, [_PP]),
+    "pfb_stream_destroy": (_I, [_S]),
     "pfb_corr_volume_build": (_I, [_P, _P, _PP, _I, _I, _I, _I, _I, _I, _I, _S]),
     "pfb_corr_volume_build_ex": (_I, [_P, _P, _PP, _I, _I, _I, _I, _I, _I, _I, C.c_float, _I, _I, _S]),
     "pfb_corr_level_bytes": (C.c_size_t, [_I, _I, _I, _I, _I]),
@@ -167,6 +170,26 @@ def dtype_code(dt: torch.dtype) -> int:
 
 def stream_ptr(device=None) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_private_streams: dict = {}
+_private_lock = threading.Lock()
+
+
+def private_stream(device) -> "torch.cuda.Stream":
+    """One stream per device that no other code can be handed: ``torch.cuda.Stream()`` draws from a pool of 32 and two
+    callers can hold the same underlying stream (a pipeline slot launching eagerly on the stream another thread is capturing
+    puts its kernels into that capture and fails its own allocations).  CUDA-graph captures run here, one at a time."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _private_lock:
+        st = _private_streams.get(idx)
+        if st is None:
+            raw = C.c_void_p()
+            with torch.cuda.device(idx):
+                check(load().pfb_stream_create(C.byref(raw)), "stream_create")
+            st = _private_streams[idx] = torch.cuda.ExternalStream(raw.value, device=torch.device("cuda", idx))
+        return st
 
 
 def require_cuda(t: torch.Tensor, name: str) -> None:

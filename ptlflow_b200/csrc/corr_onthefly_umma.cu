@@ -18,6 +18,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
+#include <stdio.h>
 
 #include "umma.cuh"
 
@@ -39,6 +41,7 @@ struct OtfArgs {
   float scale;
   int ab_fmt;
   int tiles_x, tiles_y, n_tiles;
+  unsigned long long* trace;  // PFB_OTF_TRACE: [CTA][64] clock64 stamps of the CTA's second work item (phase timeline), else null
 };
 
 struct __align__(8) OtfBars {
@@ -109,10 +112,13 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
   // work item = (query tile, level): 4x more, 4x shorter items than whole tiles -- 255 tiles on 148 SMs are 2 rounds with the
   // second one 72 % full, 1020 items are 6.9 rounds
-  for (int item = blockIdx.x; item < a.n_tiles * a.levels; item += gridDim.x) {
+  int item_no = 0;
+#define OTF_TR(slot) do { if (a.trace && item_no == 1 && (slot) < 64) a.trace[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+  for (int item = blockIdx.x; item < a.n_tiles * a.levels; item += gridDim.x, ++item_no) {
     const int tile = item / a.levels, l = item - tile * a.levels;
     const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
     __syncthreads();  // the previous item's MMAs and gathers are done: sA / sB may be overwritten
+    if (threadIdx.x == 0) OTF_TR(0);
     if (warp == 4 && lane == 0) {
       mbar_arrive_expect_tx(&bars->a_full, a.kchunks * kOtfTileBytes);
       for (int k = 0; k < a.kchunks; ++k) tma_load_4d(sA + k * kOtfTileBytes, &tmA, &bars->a_full, k * 64, tx * 16, ty * 8, b);
@@ -185,6 +191,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
       __syncthreads();  // region known to everybody (and the staging rows of the previous level have been written out)
       const int bx0 = bars->bx0, by0 = bars->by0, nb = bars->nb;
+      if (threadIdx.x == 0) { OTF_TR(1); if (a.trace && item_no == 1) a.trace[blockIdx.x * 64 + 2] = (unsigned long long)nb; }
       const int cxo = x0 - bx0, ryo = y0 - by0;  // column / row of the window's first tap inside the region
       // a window the region cannot hold: too far right of the anchor, or below the last band
       const bool outlier = live && (cxo + D > kOtfRW || ryo + D - 1 > 7 * nb);
@@ -199,6 +206,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         if (kb > 0) __syncthreads();  // everybody is done with the previous band's dump (it aliases sB)
         if (warp == 4) {
           if (lane == 0) {
+            OTF_TR(8 + kb * 6 + 0);
             mbar_arrive_expect_tx(&bars->b_full, a.kchunks * 2 * kOtfTileBytes);
             for (int k = 0; k < a.kchunks; ++k)
               tma_load_4d(sB + k * 2 * kOtfTileBytes, tmB, &bars->b_full, k * 64, bx0, by0 + 7 * kb, b);
@@ -207,6 +215,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if (lane == 0) {
             if (!a_waited) mbar_wait(&bars->a_full, par_a);
             mbar_wait(&bars->b_full, par_b);
+            OTF_TR(8 + kb * 6 + 1);
             tc_fence_after();
             const uint32_t idesc = make_idesc_f16(128, 256, a.ab_fmt);
             for (int k = 0; k < a.kchunks; ++k) {
@@ -220,6 +229,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         } else {
           // ---- epilogue: accumulator row -> shared memory (scaled by the blend weights later; storage-type rounding) ----
           mbar_wait(&bars->acc_full, par_acc);
+          if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 2);
           tc_fence_after();
           uint8_t* drow = sB + q_local * kOtfDumpPitch;  // 528-byte rows: the 32 lanes' 16-byte stores fall on 32 different bank groups
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -239,6 +249,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             }
           }
           tc_fence_before();
+          if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 3);
           // ---- gather: the window rows j whose tap pair (region rows ryo + j, ryo + j + 1) lies in this band ----
           if (mine) {
             const unsigned short* dr = reinterpret_cast<const unsigned short*>(drow);
@@ -258,6 +269,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 orow[i * K + j] = otf_f32_to_bits<T>(w00 * up[i] + w10 * up[i + 1] + w01 * dn[i] + w11 * dn[i + 1]);
             }
           }
+          if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 4);
           fence_proxy_async();  // this thread's generic-proxy accesses of the dump precede the next band's TMA writes to the same bytes
         }
         a_waited = true;
@@ -276,6 +288,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           for (int c = lane; c < KK; c += 32) dst[c] = src[c];
         }
         named_barrier_sync(1, 128);  // sOut is free for the next level
+        if (threadIdx.x == 0) OTF_TR(3);
       }
     }
     if (a_waited) par_a ^= 1;
@@ -289,6 +302,7 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       for (int c = a.levels * KK; c < a.out_stride; ++c) dst[c] = 0;
     }
   }
+#undef OTF_TR
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<256>(tmem_base);
@@ -336,6 +350,12 @@ int corr_onthefly_umma(const void* fmap1, void* const* pyr, const float* coords,
   const size_t smem = (size_t)a.kchunks * kOtfTileBytes + b_bytes + ((128 * 82 * 2 + 15) & ~15) + sizeof(OtfBars) + 1024;
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
+  // PFB_OTF_TRACE=<file>: per-CTA phase timeline of the second work item (clock64 at the role hand-overs), appended as JSON lines
+  static const char* trace_path = getenv("PFB_OTF_TRACE");
+  if (trace_path) {
+    PFB_CUDA(cudaMalloc(&a.trace, (size_t)grid * 64 * sizeof(unsigned long long)));
+    PFB_CUDA(cudaMemsetAsync(a.trace, 0, (size_t)grid * 64 * sizeof(unsigned long long), s));
+  }
   {
     ProfScope prof(KC_ONTHEFLY, s);
     if (dt == PFB_F16) {
@@ -346,6 +366,18 @@ int corr_onthefly_umma(const void* fmap1, void* const* pyr, const float* coords,
       corr_onthefly_umma_kernel<__nv_bfloat16, 4><<<grid, 192, smem, s>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], a);
     }
     PFB_LAUNCH_CHECK();
+  }
+  if (trace_path) {
+    std::vector<unsigned long long> host((size_t)grid * 64);
+    PFB_CUDA(cudaStreamSynchronize(s));
+    PFB_CUDA(cudaMemcpy(host.data(), a.trace, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    PFB_CUDA(cudaFree(a.trace));
+    if (FILE* f = fopen(trace_path, "a")) {
+      fprintf(f, "{\"grid\": %d, \"kchunks\": %d, \"H\": %d, \"W\": %d, \"stamps\": [", grid, a.kchunks, H, W);
+      for (size_t i = 0; i < host.size(); ++i) fprintf(f, "%s%llu", i ? "," : "", host[i]);
+      fprintf(f, "]}\n");
+      fclose(f);
+    }
   }
   // queries whose windows did not fit their tile's region: the SIMT kernel, one warp per flagged query
   return corr_onthefly_simt_flagged(fmap1, pyr, coords, out, flags, B, H, W, C, levels, 4, dt, out_stride, s);

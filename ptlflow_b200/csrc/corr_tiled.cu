@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(kTlWarps * 32) corr_lookup_tiled_kernel(const 
   constexpr int LVP = D * ROWP;            // halfs per staged level
   constexpr int PLANES = LEVELS * KK;
   constexpr int OUTP = (PLANES + 7) / 8 * 8;
-  constexpr int NPOS = (KK + 31) / 32;     // output positions per lane and level
+  constexpr int NPOS = K == 9 ? 3 : (K + 3) / 4;  // output positions per lane and level (rounds of 8 rows x 4 columns, see phase 2)
   static_assert(D * 3 <= 32, "one (window row, chunk) slot per lane");
+  static_assert(K <= 9, "phase 2 covers windows of up to 9 x 9 positions");
   __shared__ __align__(16) unsigned short stage[kTlWarps][LEVELS * LVP];
   __shared__ __align__(16) unsigned short orow[kTlWarps][OUTP];
 
@@ -72,27 +73,39 @@ __global__ void __launch_bounds__(kTlWarps * 32) corr_lookup_tiled_kernel(const 
   // ---- phase 1: lane = (window row j, chunk ck), the same slot in every level; all levels' loads in flight together ----
   const int j1 = lane / 3, ck = lane - j1 * 3;
   const bool slot = lane < D * 3;
+  // Level geometry once per warp, not once per level and lane: lane (l mod 4) works out level l's window origin and
+  // bilinear fractions, the others pick them up by shuffle (phase 1 was 350 of the kernel's 550 instructions when every
+  // lane redid the floor / finite / weight arithmetic for all four levels).
+  int gx0, gy0;
+  float gfx, gfy;
+  {
+    const float sc = __uint_as_float((127u - (unsigned)(lane & 3)) << 23);  // 2^-(lane & 3), exact
+    const float x = c.x * sc, y = c.y * sc;
+    const bool finite = (fabsf(x) < 1e7f) && (fabsf(y) < 1e7f);
+    const float xf = finite ? floorf(x) : -1e6f, yf = finite ? floorf(y) : -1e6f;
+    gfx = finite ? x - xf : 0.f;
+    gfy = finite ? y - yf : 0.f;
+    gx0 = (int)xf - R;
+    gy0 = (int)yf - R;
+  }
+  const bool slot01 = slot && ck < 2;
   uint4 v[LEVELS];
   float w00[LEVELS], w10[LEVELS], w01[LEVELS], w11[LEVELS];
   int off[LEVELS];
 #pragma unroll
   for (int l = 0; l < LEVELS; ++l) {
-    const float sc = 1.0f / (float)(1 << l);
-    const float x = c.x * sc, y = c.y * sc;
-    const bool finite = (fabsf(x) < 1e7f) && (fabsf(y) < 1e7f);
-    const float xf = finite ? floorf(x) : -1e6f, yf = finite ? floorf(y) : -1e6f;
-    const float fx = finite ? x - xf : 0.f, fy = finite ? y - yf : 0.f;
+    const int x0 = __shfl_sync(0xffffffffu, gx0, l), y0 = __shfl_sync(0xffffffffu, gy0, l);
+    const float fx = __shfl_sync(0xffffffffu, gfx, l), fy = __shfl_sync(0xffffffffu, gfy, l);
     w00[l] = (1.f - fx) * (1.f - fy);
     w10[l] = fx * (1.f - fy);
     w01[l] = (1.f - fx) * fy;
     w11[l] = fx * fy;
-    const int x0 = (int)xf - R, y0 = (int)yf - R;
     const int o = x0 & 7;                  // column of the window's first tap inside its tile (two's complement: floor mod)
     off[l] = o;
     const int yy = y0 + j1, tcol = (x0 >> 3) + ck;
     v[l] = make_uint4(0u, 0u, 0u, 0u);
     // the third chunk is touched only when the 2r+2 taps starting at column o run past 16
-    if (slot && (ck < 2 || o + D > 16) && yy >= 0 && yy < lv.h[l] && tcol >= 0 && tcol < lv.tiles_x[l]) {
+    if ((slot01 || (slot && o + D > 16)) && (unsigned)yy < (unsigned)lv.h[l] && (unsigned)tcol < (unsigned)lv.tiles_x[l]) {
       const unsigned short* base = reinterpret_cast<const unsigned short*>(lv.ptr[l]) + (size_t)q * lv.map_elems[l];
       const unsigned e = ((unsigned)(yy >> 2) * (unsigned)lv.tiles_x[l] + (unsigned)tcol) * 32u + (unsigned)(yy & 3) * 8u;
       uint4 u = __ldg(reinterpret_cast<const uint4*>(base + e));
@@ -114,27 +127,39 @@ __global__ void __launch_bounds__(kTlWarps * 32) corr_lookup_tiled_kernel(const 
   }
   __syncwarp();
 
-  // ---- phase 2: lane = output positions (i, j) = lane, lane + 32, ... of the (2r+1)^2 window, the same in every level.
-  // channel = l * KK + i * K + j, i <-> x offset (x-major, corr.py:43-47) ----
+  // ---- phase 2: every lane blends NPOS output positions (i, j) of the window, the same in every level.  Lane -> position is
+  // chosen for the staging copy's banks: j = lane & 7, i = lane >> 3 (+ 4 per round) puts the 8 rows of one instruction 12 words
+  // apart and leaves 4 bank-free words between them for the <= 3 words the 4 columns span; with position = lane + 32 k, rows 0
+  // and 8 of the same instruction shared banks and every one of the 48 two-byte reads took two wavefronts (ncu r02m: the kernel
+  // was L1TEX-bound at 86 %).  channel = l * KK + i * K + j, i <-> x offset (x-major, corr.py:43-47) ----
   unsigned short* ow = orow[warp];
-  int tap[NPOS];
+  int tap[NPOS], opos[NPOS];
+  bool act[NPOS];
 #pragma unroll
   for (int k = 0; k < NPOS; ++k) {
-    const int pos = lane + 32 * k;
-    const int i = pos / K, j = pos - i * K;
-    tap[k] = j * ROWP + i;
+    int i, j;
+    if (K == 9 && k == 2) {  // what the 8-row rounds leave of a 9 x 9 window: column i = 8 (8 rows) and row j = 8 (9 columns)
+      i = lane < 8 ? 8 : lane - 8;
+      j = lane < 8 ? lane : 8;
+      act[k] = lane < 17;
+    } else {
+      i = (lane >> 3) + 4 * k;
+      j = lane & 7;
+      act[k] = j < K && i < K;
+    }
+    tap[k] = act[k] ? j * ROWP + i : 0;
+    opos[k] = i * K + j;
   }
 #pragma unroll
   for (int l = 0; l < LEVELS; ++l) {
     const unsigned short* sl = st + l * LVP + off[l];
 #pragma unroll
     for (int k = 0; k < NPOS; ++k) {
-      const int pos = lane + 32 * k;
-      if (pos < KK) {
+      if (act[k]) {
         const unsigned short* w0 = sl + tap[k];
         const float r = w00[l] * half_bits_to_f32<T>(w0[0]) + w10[l] * half_bits_to_f32<T>(w0[1]) + w01[l] * half_bits_to_f32<T>(w0[ROWP]) +
                         w11[l] * half_bits_to_f32<T>(w0[ROWP + 1]);
-        ow[l * KK + pos] = f32_to_half_bits<T>(r);
+        ow[l * KK + opos[k]] = f32_to_half_bits<T>(r);
       }
     }
   }

@@ -297,6 +297,20 @@ extern "C" PFB_API int pfb_device_arch(void) {
   return major * 10 + minor;
 }
 
+extern "C" PFB_API int pfb_stream_create(pfb_stream* out) {
+  PFB_CHECK_ARG(out, "stream_create: null pointer");
+  cudaStream_t s = nullptr;
+  PFB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *out = reinterpret_cast<pfb_stream>(s);
+  return PFB_OK;
+}
+
+extern "C" PFB_API int pfb_stream_destroy(pfb_stream stream) {
+  PFB_CHECK_ARG(stream, "stream_destroy: null stream");
+  PFB_CUDA(cudaStreamDestroy(reinterpret_cast<cudaStream_t>(stream)));
+  return PFB_OK;
+}
+
 extern "C" PFB_API int pfb_pack_conv_weight(const void* src, void* dst, int Cout, int Cin, int KH, int KW, int Cout_pad,
                                     int col_offset, pfb_dtype src_dtype, pfb_dtype dst_dtype, pfb_stream stream) {
   PFB_CHECK_ARG(src && dst, "pack_conv_weight: null pointer");

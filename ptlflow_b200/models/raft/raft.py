@@ -258,13 +258,15 @@ class RAFT(BaseModel):
             static_in.copy_(images)
             if static_init is not None:
                 static_init.copy_(flow_init)
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(cur)
             from ... import _lib
 
             lib = _lib.load()
             scratch: dict = {}  # workspaces of this graph: owned by the cache entry, so they live exactly as long as the graph
+            # the capture stream is this library's own (not from torch's pool of 32, where it could be the very stream another
+            # host thread is launching on); captures are serialised, so one per device is enough
+            side = _lib.private_stream(dev)
             with _capture_lock, torch.cuda.stream(side):
+                side.wait_stream(cur)
                 for _ in range(2):  # eager warm-up on the capture stream: cuDNN autotune, weight packing, scratch caches
                     self._forward_device(static_in, static_init, scratch)
                 side.synchronize()
