@@ -30,7 +30,9 @@ constexpr int kOtfTileBytes = 128 * 128;       // 128 rows x 64 channels
 constexpr int kOtfBandRows = 256;              // targets per band: 8 rows x 32 columns
 constexpr int kOtfMaxBands = 8;                // 7 * 8 + 1 = 57 region rows at most
 constexpr int kOtfRW = 32;
-constexpr int kOtfDumpPitch = 528;             // bytes per accumulator-dump row (256 targets x 2 bytes + 16)
+constexpr int kOtfDumpPitch = 520;             // bytes per accumulator-dump row: 256 targets x 2 bytes + 8 (130 words: 8-byte stores of a
+                                               // half-warp and the gather's 4-byte loads of a warp spread over the banks)
+constexpr int kOtfMaxStages = 4;               // B-operand ring: 64-channel chunks of one band (32 KB each)
 
 struct OtfArgs {
   const float* coords;
@@ -41,13 +43,17 @@ struct OtfArgs {
   float scale;
   int ab_fmt;
   int tiles_x, tiles_y, n_tiles;
+  int b_stages;
   unsigned long long* trace;  // PFB_OTF_TRACE: [CTA][64] clock64 stamps of the CTA's second work item (phase timeline), else null
 };
 
 struct __align__(8) OtfBars {
-  uint64_t a_full, b_full, acc_full;
+  uint64_t a_full, a_empty;
+  uint64_t b_full[kOtfMaxStages], b_empty[kOtfMaxStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t reg_full[2], reg_empty[2];
   uint32_t tmem_base;
-  int bx0, by0, nb, any;
+  int region[2][4];  // per item parity: bx0, by0, number of bands
   int red[4][3];
 };
 
@@ -76,8 +82,20 @@ __device__ __forceinline__ unsigned short otf_f32_to_bits<__half>(float v) { ret
 template <>
 __device__ __forceinline__ unsigned short otf_f32_to_bits<__nv_bfloat16>(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
+// Roles: warps 0-7 = epilogue (two threads per query of the tile: warps w and w + 4 share a TMEM lane quarter and split the
+// accumulator columns / window rows), warp 8 = TMA producer, warp 9 = MMA issuer.  The three walk the
+// same list of work items (tile, level) and are coupled only through mbarriers:
+//   reg_full / reg_empty [item parity]  the epilogue publishes the item's region (anchor, bands) one item AHEAD, so the
+//                                       producer streams the next item's operands while the epilogue still blends this one
+//   a_full / a_empty                    the tile's query vectors (kchunks x 16 KB), loaded once per item
+//   b_full / b_empty [stage]            ring of 64-channel chunks of a band (32 KB each): a band's chunks are consumed once,
+//                                       so the band is never resident as a whole
+//   acc_full / acc_empty [2]            two 256-column accumulators in TMEM: band k+1 is multiplied while band k is dumped
+// (The first version ran TMA -> MMA -> dump -> gather in lock step per band with the dump aliasing the operand buffer:
+// per-CTA timelines, PFB_OTF_TRACE, showed 1.7 k + 2.3 k + 1.2 k + 2.6 k clk per band and 9.6 k clk of output loop per item; the
+// pipelined version with four epilogue warps was bound by them: 1.2 k dump + 2.4 k gather per band against 2.3 k of MMAs.)
 template <typename T, int R>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                           const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
                           const __grid_constant__ CUtensorMap tmB3, const OtfArgs a) {
@@ -86,20 +104,29 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                       // kchunks x 16 KB
-  uint8_t* sB = sA + a.kchunks * kOtfTileBytes;             // kchunks x 32 KB (>= 64 KB); after the MMAs: the accumulator dump [128][256]
-  const int b_bytes = a.kchunks * 2 * kOtfTileBytes < 128 * kOtfDumpPitch ? 5 * kOtfTileBytes : a.kchunks * 2 * kOtfTileBytes;
-  unsigned short* sOut = reinterpret_cast<unsigned short*>(sB + b_bytes);  // [128][SP] staged outputs of one level
+  uint8_t* sB = sA + a.kchunks * kOtfTileBytes;             // b_stages x 32 KB
+  uint8_t* sD = sB + a.b_stages * 2 * kOtfTileBytes;        // accumulator dump [128 queries][256 targets] (storage type), pitch 520 B
+  unsigned short* sOut = reinterpret_cast<unsigned short*>(sD + 128 * kOtfDumpPitch);  // [128][SP] staged outputs of one level
   OtfBars* bars = reinterpret_cast<OtfBars*>(reinterpret_cast<uint8_t*>(sOut) + ((128 * SP * 2 + 15) & ~15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(&bars->a_full, 1);
-    mbar_init(&bars->b_full, 1);
-    mbar_init(&bars->acc_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    for (int s = 0; s < kOtfMaxStages; ++s) {
+      mbar_init(&bars->b_full[s], 1);
+      mbar_init(&bars->b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->acc_full[s], 1);
+      mbar_init(&bars->acc_empty[s], 8);  // one arrival per epilogue warp
+      mbar_init(&bars->reg_full[s], 1);
+      mbar_init(&bars->reg_empty[s], 2);  // producer + MMA issuer have read the slot
+    }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<256>(&bars->tmem_base);
-  if (warp == 4 && lane == 0) {
+  if (warp == 9) tmem_alloc<512>(&bars->tmem_base);
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB0);
   }
@@ -107,205 +134,279 @@ corr_onthefly_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const int q_local = threadIdx.x;  // epilogue threads: 0..127 = (row in tile) * 16 + (column in tile)
-  uint32_t par_a = 0, par_b = 0, par_acc = 0;
+  const int n_items = a.n_tiles * a.levels;
+#define OTF_TR(slot) do { if (a.trace && n == 1 && (slot) < 64) a.trace[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
 
-  // work item = (query tile, level): 4x more, 4x shorter items than whole tiles -- 255 tiles on 148 SMs are 2 rounds with the
-  // second one 72 % full, 1020 items are 6.9 rounds
-  int item_no = 0;
-#define OTF_TR(slot) do { if (a.trace && item_no == 1 && (slot) < 64) a.trace[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
-  for (int item = blockIdx.x; item < a.n_tiles * a.levels; item += gridDim.x, ++item_no) {
-    const int tile = item / a.levels, l = item - tile * a.levels;
-    const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
-    __syncthreads();  // the previous item's MMAs and gathers are done: sA / sB may be overwritten
-    if (threadIdx.x == 0) OTF_TR(0);
-    if (warp == 4 && lane == 0) {
-      mbar_arrive_expect_tx(&bars->a_full, a.kchunks * kOtfTileBytes);
-      for (int k = 0; k < a.kchunks; ++k) tma_load_4d(sA + k * kOtfTileBytes, &tmA, &bars->a_full, k * 64, tx * 16, ty * 8, b);
+  if (warp == 8) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t phb = 0;
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int slot = n & 1;
+        mbar_wait(&bars->reg_full[slot], (n >> 1) & 1);
+        const int bx0 = bars->region[slot][0], by0 = bars->region[slot][1], nb = bars->region[slot][2];
+        mbar_arrive(&bars->reg_empty[slot]);
+        const int tile = item / a.levels, l = item - tile * a.levels;
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
+        const CUtensorMap* tmB = l == 0 ? &tmB0 : (l == 1 ? &tmB1 : (l == 2 ? &tmB2 : &tmB3));
+        mbar_wait(&bars->a_empty, (n & 1) ^ 1);  // the previous item's MMAs are done with the query tile
+        mbar_arrive_expect_tx(&bars->a_full, a.kchunks * kOtfTileBytes);
+        for (int k = 0; k < a.kchunks; ++k) tma_load_4d(sA + k * kOtfTileBytes, &tmA, &bars->a_full, k * 64, tx * 16, ty * 8, b);
+        for (int kb = 0; kb < nb; ++kb) {
+          OTF_TR(8 + kb * 6 + 0);
+          for (int k = 0; k < a.kchunks; ++k) {
+            mbar_wait(&bars->b_empty[sb], phb ^ 1);
+            mbar_arrive_expect_tx(&bars->b_full[sb], 2 * kOtfTileBytes);
+            tma_load_4d(sB + sb * 2 * kOtfTileBytes, tmB, &bars->b_full[sb], k * 64, bx0, by0 + 7 * kb, b);
+            if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+          }
+        }
+      }
     }
-    // ---- this thread's query ----
-    const int qy = ty * 8 + (q_local >> 4), qx = tx * 16 + (q_local & 15);
-    const bool q_in = warp < 4 && qy < a.H && qx < a.W;
-    const size_t q = ((size_t)b * a.H + (q_in ? qy : 0)) * a.W + (q_in ? qx : 0);
-    float cx = 0.f, cy = 0.f;
-    if (q_in) {
-      const float2 c = __ldg(reinterpret_cast<const float2*>(a.coords) + q);
-      cx = c.x;
-      cy = c.y;
+  } else if (warp == 9) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 256, a.ab_fmt);
+      int sb = 0, g = 0;
+      uint32_t phb = 0;
+      int n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int slot = n & 1;
+        mbar_wait(&bars->reg_full[slot], (n >> 1) & 1);
+        const int nb = bars->region[slot][2];
+        mbar_arrive(&bars->reg_empty[slot]);
+        mbar_wait(&bars->a_full, n & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nb; ++kb, ++g) {
+          const int t = g & 1;
+          mbar_wait(&bars->acc_empty[t], ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + t * 256;
+          for (int k = 0; k < a.kchunks; ++k) {
+            mbar_wait(&bars->b_full[sb], phb);
+            tc_fence_after();
+            const uint64_t da = make_desc_k_sw128(smem_u32(sA + k * kOtfTileBytes));
+            const uint64_t db = make_desc_k_sw128(smem_u32(sB + sb * 2 * kOtfTileBytes));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_f16(d, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, (k | kk) != 0);
+            umma_commit(&bars->b_empty[sb]);
+            if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+          }
+          OTF_TR(8 + kb * 6 + 1);
+          umma_commit(&bars->acc_full[t]);
+        }
+        umma_commit(&bars->a_empty);  // arrives once every MMA issued so far has read its operands
+      }
     }
-    bool a_waited = false;
-    {
-      const CUtensorMap* tmB = l == 0 ? &tmB0 : (l == 1 ? &tmB1 : (l == 2 ? &tmB2 : &tmB3));
-      const int Hl = a.lh[l], Wl = a.lw[l];
-      // ---- window geometry of this query at this level ----
-      int x0 = 0, y0 = 0;
-      float w00 = 0.f, w10 = 0.f, w01 = 0.f, w11 = 0.f;
-      bool live = false;  // the window overlaps the map (otherwise all 81 outputs are zero)
-      if (q_in) {
-        const float sc = 1.0f / (float)(1 << l);
-        const float x = cx * sc, y = cy * sc;
+  } else {
+    // ================= epilogue: region, accumulator dump, window blend, output =================
+    const int q_local = threadIdx.x & 127;  // (row in tile) * 16 + (column in tile)
+    const int half = threadIdx.x >> 7;      // 0 / 1: which half of the accumulator columns and which window rows this thread takes
+    struct Geom {
+      int x0, y0, b, tx, ty, l;
+      float w00, w10, w01, w11;
+      bool q_in, live;
+      size_t q;
+    };
+    // window geometry of this thread's query for an item
+    auto geometry = [&](int item, Geom& g) {
+      const int tile = item / a.levels;
+      g.l = item - tile * a.levels;
+      g.tx = tile % a.tiles_x;
+      g.ty = (tile / a.tiles_x) % a.tiles_y;
+      g.b = tile / (a.tiles_x * a.tiles_y);
+      const int qy = g.ty * 8 + (q_local >> 4), qx = g.tx * 16 + (q_local & 15);
+      g.q_in = qy < a.H && qx < a.W;
+      g.q = ((size_t)g.b * a.H + (g.q_in ? qy : 0)) * a.W + (g.q_in ? qx : 0);
+      g.x0 = g.y0 = 0;
+      g.w00 = g.w10 = g.w01 = g.w11 = 0.f;
+      g.live = false;  // the window overlaps the map (otherwise all 81 outputs are zero)
+      if (g.q_in) {
+        const float2 c = __ldg(reinterpret_cast<const float2*>(a.coords) + g.q);
+        const float sc = 1.0f / (float)(1 << g.l);
+        const float x = c.x * sc, y = c.y * sc;
         const bool finite = (fabsf(x) < 1e7f) && (fabsf(y) < 1e7f);
         const float xf = finite ? floorf(x) : -1e6f, yf = finite ? floorf(y) : -1e6f;
         const float fx = finite ? x - xf : 0.f, fy = finite ? y - yf : 0.f;
-        w00 = (1.f - fx) * (1.f - fy) * a.scale;
-        w10 = fx * (1.f - fy) * a.scale;
-        w01 = (1.f - fx) * fy * a.scale;
-        w11 = fx * fy * a.scale;
-        x0 = (int)xf - R;
-        y0 = (int)yf - R;
-        live = x0 + D - 1 >= 0 && x0 < Wl && y0 + D - 1 >= 0 && y0 < Hl;
+        g.w00 = (1.f - fx) * (1.f - fy) * a.scale;
+        g.w10 = fx * (1.f - fy) * a.scale;
+        g.w01 = (1.f - fx) * fy * a.scale;
+        g.w11 = fx * fy * a.scale;
+        g.x0 = (int)xf - R;
+        g.y0 = (int)yf - R;
+        // (selects, not a.lw[g.l]: a dynamic index into the kernel parameters makes ptxas copy them to a stack frame)
+        const int Wl = g.l == 0 ? a.lw[0] : (g.l == 1 ? a.lw[1] : (g.l == 2 ? a.lw[2] : a.lw[3]));
+        const int Hl = g.l == 0 ? a.lh[0] : (g.l == 1 ? a.lh[1] : (g.l == 2 ? a.lh[2] : a.lh[3]));
+        g.live = g.x0 + D - 1 >= 0 && g.x0 < Wl && g.y0 + D - 1 >= 0 && g.y0 < Hl;
       }
-      // ---- region of the item: anchored at the smallest window origin of the live queries ----
-      if (warp < 4) {
-        int mx = live ? x0 : 0x7fffffff, my = live ? y0 : 0x7fffffff, My = live ? y0 : -0x7fffffff;
+    };
+    // region of item number n: anchored at the smallest window origin of the live queries; published for the other two roles
+    auto publish = [&](int n, const Geom& g) {
+      int mx = g.live ? g.x0 : 0x7fffffff, my = g.live ? g.y0 : 0x7fffffff, My = g.live ? g.y0 : -0x7fffffff;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-          my = min(my, __shfl_xor_sync(0xffffffffu, my, o));
-          My = max(My, __shfl_xor_sync(0xffffffffu, My, o));
-        }
-        if (lane == 0) {
-          bars->red[warp][0] = mx;
-          bars->red[warp][1] = my;
-          bars->red[warp][2] = My;
-        }
-        named_barrier_sync(1, 128);
-        if (threadIdx.x == 0) {
-          int bx = 0x7fffffff, by = 0x7fffffff, By = -0x7fffffff;
-          for (int w = 0; w < 4; ++w) {
-            bx = min(bx, bars->red[w][0]);
-            by = min(by, bars->red[w][1]);
-            By = max(By, bars->red[w][2]);
-          }
-          const int any = bx != 0x7fffffff;
-          int nb = 0;
-          if (any) {
-            nb = (By + D - 1 - by + 6) / 7;  // bands of 8 rows at stride 7 that cover region rows 0 .. By + D - 1 - by
-            nb = nb < 1 ? 1 : (nb > kOtfMaxBands ? kOtfMaxBands : nb);
-          }
-          bars->bx0 = bx;
-          bars->by0 = by;
-          bars->nb = nb;
-          bars->any = any;
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = min(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        my = min(my, __shfl_xor_sync(0xffffffffu, my, o));
+        My = max(My, __shfl_xor_sync(0xffffffffu, My, o));
       }
-      __syncthreads();  // region known to everybody (and the staging rows of the previous level have been written out)
-      const int bx0 = bars->bx0, by0 = bars->by0, nb = bars->nb;
-      if (threadIdx.x == 0) { OTF_TR(1); if (a.trace && item_no == 1) a.trace[blockIdx.x * 64 + 2] = (unsigned long long)nb; }
-      const int cxo = x0 - bx0, ryo = y0 - by0;  // column / row of the window's first tap inside the region
-      // a window the region cannot hold: too far right of the anchor, or below the last band
-      const bool outlier = live && (cxo + D > kOtfRW || ryo + D - 1 > 7 * nb);
-      if (q_in && outlier) a.flags[q] = 1;
-      const bool mine = live && !outlier;
-      unsigned short* orow = sOut + q_local * SP;
-      if (warp < 4 && !mine) {
-#pragma unroll 9
-        for (int c = 0; c < KK; ++c) orow[c] = 0;  // zero window (or a flagged query: its row is rewritten by the SIMT pass)
+      if (lane == 0 && warp < 4) {
+        bars->red[warp][0] = mx;
+        bars->red[warp][1] = my;
+        bars->red[warp][2] = My;
       }
-      for (int kb = 0; kb < nb; ++kb) {
-        if (kb > 0) __syncthreads();  // everybody is done with the previous band's dump (it aliases sB)
-        if (warp == 4) {
-          if (lane == 0) {
-            OTF_TR(8 + kb * 6 + 0);
-            mbar_arrive_expect_tx(&bars->b_full, a.kchunks * 2 * kOtfTileBytes);
-            for (int k = 0; k < a.kchunks; ++k)
-              tma_load_4d(sB + k * 2 * kOtfTileBytes, tmB, &bars->b_full, k * 64, bx0, by0 + 7 * kb, b);
-          }
-        } else if (warp == 5) {
-          if (lane == 0) {
-            if (!a_waited) mbar_wait(&bars->a_full, par_a);
-            mbar_wait(&bars->b_full, par_b);
-            OTF_TR(8 + kb * 6 + 1);
-            tc_fence_after();
-            const uint32_t idesc = make_idesc_f16(128, 256, a.ab_fmt);
-            for (int k = 0; k < a.kchunks; ++k) {
-              const uint64_t da = make_desc_k_sw128(smem_u32(sA + k * kOtfTileBytes));
-              const uint64_t db = make_desc_k_sw128(smem_u32(sB + k * 2 * kOtfTileBytes));
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, (k | kk) != 0);
-            }
-            umma_commit(&bars->acc_full);
-          }
+      named_barrier_sync(1, 256);
+      if (threadIdx.x == 0) {
+        int bx = 0x7fffffff, by = 0x7fffffff, By = -0x7fffffff;
+        for (int w = 0; w < 4; ++w) {  // warps 4-7 hold the same queries
+          bx = min(bx, bars->red[w][0]);
+          by = min(by, bars->red[w][1]);
+          By = max(By, bars->red[w][2]);
+        }
+        int nb = 0;
+        if (bx != 0x7fffffff) {
+          nb = (By + D - 1 - by + 6) / 7;  // bands of 8 rows at stride 7 that cover region rows 0 .. By + D - 1 - by
+          nb = nb < 1 ? 1 : (nb > kOtfMaxBands ? kOtfMaxBands : nb);
         } else {
-          // ---- epilogue: accumulator row -> shared memory (scaled by the blend weights later; storage-type rounding) ----
-          mbar_wait(&bars->acc_full, par_acc);
-          if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 2);
-          tc_fence_after();
-          uint8_t* drow = sB + q_local * kOtfDumpPitch;  // 528-byte rows: the 32 lanes' 16-byte stores fall on 32 different bank groups
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 u;
-              u.x = otf_pack2<T>(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
-              u.y = otf_pack2<T>(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-              u.z = otf_pack2<T>(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-              u.w = otf_pack2<T>(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-              *reinterpret_cast<uint4*>(drow + (((c << 2) | g) << 4)) = u;
-            }
-          }
-          tc_fence_before();
-          if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 3);
-          // ---- gather: the window rows j whose tap pair (region rows ryo + j, ryo + j + 1) lies in this band ----
-          if (mine) {
-            const unsigned short* dr = reinterpret_cast<const unsigned short*>(drow);
-#pragma unroll 1
-            for (int j = 0; j < K; ++j) {
-              const int rr = ryo + j - 7 * kb;  // region row of the upper tap, relative to the band
-              if (rr < 0 || rr > 6) continue;
-              float up[D], dn[D];
-#pragma unroll
-              for (int i = 0; i < D; ++i) {
-                const int e0 = rr * kOtfRW + cxo + i, e1 = e0 + kOtfRW;
-                up[i] = otf_bits_to_f32<T>(dr[e0]);
-                dn[i] = otf_bits_to_f32<T>(dr[e1]);
-              }
-#pragma unroll
-              for (int i = 0; i < K; ++i)
-                orow[i * K + j] = otf_f32_to_bits<T>(w00 * up[i] + w10 * up[i + 1] + w01 * dn[i] + w11 * dn[i + 1]);
-            }
-          }
-          if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 4);
-          fence_proxy_async();  // this thread's generic-proxy accesses of the dump precede the next band's TMA writes to the same bytes
+          bx = by = 0;
         }
-        a_waited = true;
-        par_b ^= 1;
-        par_acc ^= 1;
+        const int slot = n & 1;
+        mbar_wait(&bars->reg_empty[slot], ((n >> 1) & 1) ^ 1);  // item n - 2's region has been read by both consumers
+        bars->region[slot][0] = bx;
+        bars->region[slot][1] = by;
+        bars->region[slot][2] = nb;
+        mbar_arrive(&bars->reg_full[slot]);
       }
-      // ---- the level's 81 outputs of the 128 queries: coalesced 2-byte runs (81 consecutive channels per query) ----
-      if (warp < 4) {
-        named_barrier_sync(1, 128);
-        unsigned short* outp = reinterpret_cast<unsigned short*>(a.out);
-        for (int rq = warp; rq < 128; rq += 4) {
-          const int yy = ty * 8 + (rq >> 4), xx = tx * 16 + (rq & 15);
-          if (yy >= a.H || xx >= a.W) continue;
-          unsigned short* dst = outp + (((size_t)b * a.H + yy) * a.W + xx) * a.out_stride + l * KK;
-          const unsigned short* src = sOut + rq * SP;
-          for (int c = lane; c < KK; c += 32) dst[c] = src[c];
-        }
-        named_barrier_sync(1, 128);  // sOut is free for the next level
-        if (threadIdx.x == 0) OTF_TR(3);
-      }
+      named_barrier_sync(1, 256);  // region[slot] readable by the epilogue threads; red[] free again
+    };
+
+    Geom cur, nxt;
+    int n = 0, g = 0;
+    int item = blockIdx.x;
+    if (item < n_items) {
+      geometry(item, cur);
+      publish(0, cur);
     }
-    if (a_waited) par_a ^= 1;
-    else if (warp == 5 && lane == 0) {  // no level had a live window: the A tile was loaded but never consumed
-      mbar_wait(&bars->a_full, par_a);
-      par_a ^= 1;
-    } else par_a ^= 1;
-    // pad columns of the pixel-major rows (out_stride > levels * 81): zero
-    if (warp < 4 && q_in && l == 0) {
-      unsigned short* dst = reinterpret_cast<unsigned short*>(a.out) + q * a.out_stride;
-      for (int c = a.levels * KK; c < a.out_stride; ++c) dst[c] = 0;
+    for (; item < n_items; item += gridDim.x, ++n) {
+      if (threadIdx.x == 0) OTF_TR(0);
+      const int next_item = item + gridDim.x;
+      if (next_item < n_items) {  // one item ahead: the producer fetches its operands during this item's blends
+        geometry(next_item, nxt);
+        publish(n + 1, nxt);
+      }
+      if (threadIdx.x == 0) OTF_TR(1);
+      const int bx0 = bars->region[n & 1][0], by0 = bars->region[n & 1][1], nb = bars->region[n & 1][2];
+      if (threadIdx.x == 0 && a.trace && n == 1) a.trace[blockIdx.x * 64 + 2] = (unsigned long long)nb;
+      const int cxo = cur.x0 - bx0, ryo = cur.y0 - by0;  // column / row of the window's first tap inside the region
+      // a window the region cannot hold: too far right of the anchor, or below the last band
+      const bool outlier = cur.live && (cxo + D > kOtfRW || ryo + D - 1 > 7 * nb);
+      if (cur.q_in && outlier && half == 0) a.flags[cur.q] = 1;
+      const bool mine = cur.live && !outlier;
+      unsigned short* orow = sOut + q_local * SP;
+      if (!mine) {
+        for (int c = half; c < KK; c += 2) orow[c] = 0;  // zero window (or a flagged query: its row is rewritten by the SIMT pass)
+      }
+      const float w00 = cur.w00, w10 = cur.w10, w01 = cur.w01, w11 = cur.w11;
+      uint8_t* drow = sD + q_local * kOtfDumpPitch;
+      for (int kb = 0; kb < nb; ++kb, ++g) {
+        const int t = g & 1;
+        // ---- accumulator row -> shared memory (storage-type rounding, the rounding the materialised volume has) ----
+        mbar_wait(&bars->acc_full[t], (g >> 1) & 1);
+        if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 2);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + t * 256 + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+        for (int c = 4 * half; c < 4 * half + 4; ++c) {  // this thread's half of the band: region rows 4 half .. 4 half + 3
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            uint2 u;
+            u.x = otf_pack2<T>(__uint_as_float(r[4 * e + 0]), __uint_as_float(r[4 * e + 1]));
+            u.y = otf_pack2<T>(__uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+            *reinterpret_cast<uint2*>(drow + (((c << 3) | e) << 3)) = u;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty[t]);  // the issuer may overwrite this accumulator (band kb + 2)
+        named_barrier_sync(2, 256);  // the other half of this query's dump row is written
+        if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 3);
+        // ---- gather: the window rows j (of this thread's parity) whose tap pair (region rows ryo + j, ryo + j + 1) lies in
+        // this band.  4-byte loads of the aligned words that cover the 2r+2 taps, realigned by a funnel shift ----
+        if (mine) {
+          const uint32_t* dr = reinterpret_cast<const uint32_t*>(drow);
+          const uint32_t sh = (uint32_t)(cxo & 1) * 16u;
+#pragma unroll 1
+          for (int j = half; j < K; j += 2) {
+            const int rr = ryo + j - 7 * kb;  // region row of the upper tap, relative to the band
+            if (rr < 0 || rr > 6) continue;
+            const uint32_t* p0 = dr + ((rr * kOtfRW + cxo) >> 1);
+            uint32_t wu[D / 2 + 1], wd[D / 2 + 1];
+#pragma unroll
+            for (int i = 0; i <= D / 2; ++i) {
+              wu[i] = p0[i];
+              wd[i] = p0[i + kOtfRW / 2];
+            }
+            float up[D], dn[D];
+#pragma unroll
+            for (int i = 0; i < D / 2; ++i) {
+              const uint32_t vu = __funnelshift_r(wu[i], wu[i + 1], sh), vd = __funnelshift_r(wd[i], wd[i + 1], sh);
+              up[2 * i] = otf_bits_to_f32<T>((unsigned short)(vu & 0xFFFFu));
+              up[2 * i + 1] = otf_bits_to_f32<T>((unsigned short)(vu >> 16));
+              dn[2 * i] = otf_bits_to_f32<T>((unsigned short)(vd & 0xFFFFu));
+              dn[2 * i + 1] = otf_bits_to_f32<T>((unsigned short)(vd >> 16));
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+              orow[i * K + j] = otf_f32_to_bits<T>(w00 * up[i] + w10 * up[i + 1] + w01 * dn[i] + w11 * dn[i + 1]);
+          }
+        }
+        if (threadIdx.x == 0) OTF_TR(8 + kb * 6 + 4);
+        if (kb + 1 < nb) named_barrier_sync(2, 256);  // both threads of a query are done with its dump row before the next band lands in it
+      }
+      // ---- the level's 81 outputs of the 128 queries: coalesced 2-byte runs (81 consecutive channels per query), four rows
+      // per round so that a warp has 12 loads, then 12 stores in flight ----
+      named_barrier_sync(1, 256);
+      {
+        unsigned short* outp = reinterpret_cast<unsigned short*>(a.out);
+        for (int r0 = warp; r0 < 128; r0 += 32) {
+          unsigned short v[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned short* src = sOut + (r0 + 8 * u) * SP;
+            v[u][0] = src[lane];
+            v[u][1] = src[lane + 32];
+            v[u][2] = lane + 64 < KK ? src[lane + 64] : (unsigned short)0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rq = r0 + 8 * u;
+            const int yy = cur.ty * 8 + (rq >> 4), xx = cur.tx * 16 + (rq & 15);
+            if (yy >= a.H || xx >= a.W) continue;
+            unsigned short* dst = outp + (((size_t)cur.b * a.H + yy) * a.W + xx) * a.out_stride + cur.l * KK;
+            dst[lane] = v[u][0];
+            dst[lane + 32] = v[u][1];
+            if (lane + 64 < KK) dst[lane + 64] = v[u][2];
+          }
+        }
+      }
+      named_barrier_sync(1, 256);  // sOut (and the dump rows) are free for the next item
+      if (threadIdx.x == 0) OTF_TR(3);
+      // pad columns of the pixel-major rows (out_stride > levels * 81): zero
+      if (cur.q_in && cur.l == 0 && half == 0) {
+        unsigned short* dst = reinterpret_cast<unsigned short*>(a.out) + cur.q * a.out_stride;
+        for (int c = a.levels * KK; c < a.out_stride; ++c) dst[c] = 0;
+      }
+      cur = nxt;
     }
   }
 #undef OTF_TR
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<256>(tmem_base);
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -346,8 +447,16 @@ int corr_onthefly_umma(const void* fmap1, void* const* pyr, const float* coords,
     if (rc) return rc;
   }
   PFB_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * H * W, s));
-  const int b_bytes = a.kchunks * 2 * kOtfTileBytes < 128 * kOtfDumpPitch ? 5 * kOtfTileBytes : a.kchunks * 2 * kOtfTileBytes;
-  const size_t smem = (size_t)a.kchunks * kOtfTileBytes + b_bytes + ((128 * 82 * 2 + 15) & ~15) + sizeof(OtfBars) + 1024;
+  // shared memory: query tile + operand ring + accumulator dump + output staging; the ring takes what is left (2 stages at C = 256)
+  const size_t fixed = (size_t)a.kchunks * kOtfTileBytes + 128 * kOtfDumpPitch + ((128 * 82 * 2 + 15) & ~15) + sizeof(OtfBars) + 1024;
+  int stages = (int)((227 * 1024 - fixed) / (2 * kOtfTileBytes));
+  if (stages > kOtfMaxStages) stages = kOtfMaxStages;
+  if (stages < 2) {
+    set_error("corr_lookup_onthefly_tc: no room for the operand ring (C=%d)", C);
+    return PFB_ERR_UNSUPPORTED;
+  }
+  a.b_stages = stages;
+  const size_t smem = fixed + (size_t)stages * 2 * kOtfTileBytes;
   int grid = sm_count();
   if (grid > a.n_tiles) grid = a.n_tiles;
   // PFB_OTF_TRACE=<file>: per-CTA phase timeline of the second work item (clock64 at the role hand-overs), appended as JSON lines
@@ -360,10 +469,10 @@ int corr_onthefly_umma(const void* fmap1, void* const* pyr, const float* coords,
     ProfScope prof(KC_ONTHEFLY, s);
     if (dt == PFB_F16) {
       PFB_CUDA(cudaFuncSetAttribute(corr_onthefly_umma_kernel<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      corr_onthefly_umma_kernel<__half, 4><<<grid, 192, smem, s>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], a);
+      corr_onthefly_umma_kernel<__half, 4><<<grid, 320, smem, s>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], a);
     } else {
       PFB_CUDA(cudaFuncSetAttribute(corr_onthefly_umma_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      corr_onthefly_umma_kernel<__nv_bfloat16, 4><<<grid, 192, smem, s>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], a);
+      corr_onthefly_umma_kernel<__nv_bfloat16, 4><<<grid, 320, smem, s>>>(tmA, tmB[0], tmB[1], tmB[2], tmB[3], a);
     }
     PFB_LAUNCH_CHECK();
   }

@@ -25,7 +25,54 @@ from .extractor import BasicEncoder, SmallEncoder
 from .update import BasicUpdateBlock, SmallUpdateBlock
 
 
-_capture_lock = threading.Lock()  # one CUDA-graph capture at a time per process (pipeline slots capture on their first batch)
+class _CaptureGate:
+    """Readers-writer gate between forwards and CUDA-graph captures of this process: any number of forwards (eager or
+    replayed) run together, a capture runs alone.  Host threads that launch and allocate while another thread's stream
+    is capturing (pipeline slots on their first batches) made the capture, or their own calls, fail with
+    ``cudaErrorStreamCaptureUnsupported`` now and then; captures are rare (once per shape and stream), so excluding them
+    costs nothing in steady state."""
+
+    def __init__(self) -> None:
+        self._cond = threading.Condition()
+        self._readers = 0
+        self._writer = False
+        self._writers_waiting = 0
+
+    @contextlib.contextmanager
+    def forward(self):
+        if not _GATE_FORWARDS:
+            yield
+            return
+        with self._cond:
+            while self._writer or self._writers_waiting:
+                self._cond.wait()
+            self._readers += 1
+        try:
+            yield
+        finally:
+            with self._cond:
+                self._readers -= 1
+                if self._readers == 0:
+                    self._cond.notify_all()
+
+    @contextlib.contextmanager
+    def capture(self):
+        with self._cond:
+            self._writers_waiting += 1
+            while self._writer or self._readers:
+                self._cond.wait()
+            self._writers_waiting -= 1
+            self._writer = True
+        try:
+            yield
+        finally:
+            with self._cond:
+                self._writer = False
+                self._cond.notify_all()
+
+
+_gate = _CaptureGate()  # one CUDA-graph capture at a time per process, and no forward of another host thread beside it
+_GATE_FORWARDS = bool(int(__import__("os").environ.get("PFB_CAPTURE_EXCLUSIVE", "1")))
 _cudnn_lock = threading.Lock()
 _cudnn_users = 0
 _cudnn_saved = None
@@ -192,6 +239,14 @@ class RAFT(BaseModel):
         return out
 
     def _forward_device(self, images: torch.Tensor, flow_init: Optional[torch.Tensor], scratch: Optional[dict] = None):
+        """``scratch``: a dict that owns every scratch buffer of this forward (refinement workspace, normalisation sums).  A CUDA
+        graph passes its own, so that graphs replayed side by side on different streams share nothing but read-only weights."""
+        if scratch is None:
+            return self._forward_device_impl(images, flow_init, None)
+        with ops.scratch_scope(scratch):
+            return self._forward_device_impl(images, flow_init, scratch)
+
+    def _forward_device_impl(self, images: torch.Tensor, flow_init: Optional[torch.Tensor], scratch: Optional[dict]):
         """images [B,2,3,H,W] on the device (only read) -> (flow_up fp32 [B,2,H,W], flow_small fp32 [B,2,H/8,W/8]).
         Everything in here is enqueued on the current stream with no host synchronisation and no data-dependent
         control flow, so the whole forward can be captured into one CUDA graph (``_forward_graphed``)."""
@@ -229,6 +284,40 @@ class RAFT(BaseModel):
     def _weights_signature(self) -> tuple:
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple((b.data_ptr(), b._version) for b in self.buffers())
 
+    def _capture(self, key, images: torch.Tensor, flow_init: Optional[torch.Tensor]):
+        """Two eager warm-ups, then the capture, on this library's private stream; called with the capture gate held."""
+        dev = images.device
+        cur = torch.cuda.current_stream(dev)
+        static_in = torch.empty_like(images)
+        static_init = torch.empty_like(flow_init) if flow_init is not None else None
+        static_in.copy_(images)
+        if static_init is not None:
+            static_init.copy_(flow_init)
+        from ... import _lib
+
+        lib = _lib.load()
+        scratch: dict = {}  # workspaces of this graph: owned by the cache entry, so they live exactly as long as the graph
+        # the capture stream is this library's own (not from torch's pool of 32, where it could be the very stream another
+        # host thread is launching on); captures are serialised, so one per device is enough
+        side = _lib.private_stream(dev)
+        with torch.cuda.stream(side):
+            side.wait_stream(cur)
+            for _ in range(2):  # eager warm-up on the capture stream: cuDNN autotune, weight packing, scratch caches
+                self._forward_device(static_in, static_init, scratch)
+            side.synchronize()
+            n0 = lib.pfb_launch_count(-1)
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: other host threads (pipeline slots, data loaders) keep making CUDA calls while this one captures
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                flow_up, flow_small = self._forward_device(static_in, static_init, scratch)
+            launches = int(lib.pfb_launch_count(-1) - n0)
+        cur.wait_stream(side)
+        if len(self._graphs) >= 8:  # shapes / streams come and go (infer.py, validate.py: dataset-dependent sizes)
+            self._graphs.pop(next(iter(self._graphs)))
+        ent = (graph, static_in, static_init, flow_up, flow_small, launches, scratch)
+        self._graphs[key] = ent
+        return ent
+
     def _forward_graphed(self, images: torch.Tensor, flow_init: Optional[torch.Tensor]):
         """One ``cudaGraphLaunch`` per forward.  The ~250 kernels of a forward (encoders, volume, 12 x 13 refinement
         launches, upsample) cost ~6 ms of host time when launched one by one; captured once per
@@ -250,42 +339,17 @@ class RAFT(BaseModel):
                 if len(self._graph_seen) > 64:
                     self._graph_seen.clear()
                 self._graph_seen[key] = seen + 1
-                return self._forward_device(images, flow_init), False
+                with _gate.forward():
+                    return self._forward_device(images, flow_init), False
         if ent is None:
-            cur = torch.cuda.current_stream(dev)
-            static_in = torch.empty_like(images)
-            static_init = torch.empty_like(flow_init) if flow_init is not None else None
-            static_in.copy_(images)
-            if static_init is not None:
-                static_init.copy_(flow_init)
-            from ... import _lib
-
-            lib = _lib.load()
-            scratch: dict = {}  # workspaces of this graph: owned by the cache entry, so they live exactly as long as the graph
-            # the capture stream is this library's own (not from torch's pool of 32, where it could be the very stream another
-            # host thread is launching on); captures are serialised, so one per device is enough
-            side = _lib.private_stream(dev)
-            with _capture_lock, torch.cuda.stream(side):
-                side.wait_stream(cur)
-                for _ in range(2):  # eager warm-up on the capture stream: cuDNN autotune, weight packing, scratch caches
-                    self._forward_device(static_in, static_init, scratch)
-                side.synchronize()
-                n0 = lib.pfb_launch_count(-1)
-                graph = torch.cuda.CUDAGraph()
-                # thread_local: other host threads (pipeline slots, data loaders) keep making CUDA calls while this one captures
-                with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
-                    flow_up, flow_small = self._forward_device(static_in, static_init, scratch)
-                launches = int(lib.pfb_launch_count(-1) - n0)
-            cur.wait_stream(side)
-            if len(self._graphs) >= 8:  # shapes / streams come and go (infer.py, validate.py: dataset-dependent sizes)
-                self._graphs.pop(next(iter(self._graphs)))
-            ent = (graph, static_in, static_init, flow_up, flow_small, launches, scratch)
-            self._graphs[key] = ent
+            with _gate.capture():
+                ent = self._capture(key, images, flow_init)
         graph, static_in, static_init, flow_up, flow_small, launches = ent[:6]
-        static_in.copy_(images, non_blocking=True)
-        if static_init is not None:
-            static_init.copy_(flow_init, non_blocking=True)
-        graph.replay()
+        with _gate.forward():
+            static_in.copy_(images, non_blocking=True)
+            if static_init is not None:
+                static_init.copy_(flow_init, non_blocking=True)
+            graph.replay()
         self.graph_replays += 1
         self.graph_launches_replayed += launches
         return (flow_up, flow_small), True
@@ -309,12 +373,15 @@ class RAFT(BaseModel):
             if use_graph:
                 (flow_up, flow_small), use_graph = self._forward_graphed(images, flow_init)  # (False: ran eagerly, fresh tensors)
             else:
-                flow_up, flow_small = self._forward_device(images, flow_init)
+                with _gate.forward():
+                    flow_up, flow_small = self._forward_device(images, flow_init)
             out_dtype = inputs["images"].dtype
             # .to() / clone() give the caller fresh tensors: the graph's static outputs are overwritten by the next replay
-            flows = flow_up.to(out_dtype) if out_dtype != torch.float32 else (flow_up.clone() if use_graph else flow_up)
-            small = flow_small.to(out_dtype) if out_dtype != torch.float32 else (flow_small.clone() if use_graph else flow_small)
-            return {"flows": flows[:, None], "flow_small": small, "flows_fp32": (flow_up.clone() if use_graph else flow_up)[:, None]}
+            with _gate.forward():
+                flows = flow_up.to(out_dtype) if out_dtype != torch.float32 else (flow_up.clone() if use_graph else flow_up)
+                small = flow_small.to(out_dtype) if out_dtype != torch.float32 else (flow_small.clone() if use_graph else flow_small)
+                fp32 = flow_up.clone() if use_graph else flow_up
+            return {"flows": flows[:, None], "flow_small": small, "flows_fp32": fp32[:, None]}
 
 
 class RAFTSmall(RAFT):

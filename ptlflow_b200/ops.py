@@ -7,7 +7,9 @@ channels_last.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence
 
 import torch
@@ -378,6 +380,31 @@ def preprocess_frames(images: torch.Tensor, padded_hw, pad_top_left, out_channel
 
 
 _inorm_ws = {}
+_tls = threading.local()
+
+
+@contextlib.contextmanager
+def scratch_scope(owner: Optional[dict]):
+    """While active on this host thread, the small scratch buffers of the normalisation kernels below live in ``owner`` (a dict
+    the caller keeps alive) instead of the per-stream cache.  A CUDA graph bakes the addresses of its scratch into its kernels:
+    graphs captured on the same stream and replayed concurrently on different ones must not share them, so every capture brings
+    its own dict (RAFT._capture)."""
+    prev = getattr(_tls, "owner", None)
+    _tls.owner = owner
+    try:
+        yield
+    finally:
+        _tls.owner = prev
+
+
+def _scratch(key: tuple, numel: int, device) -> torch.Tensor:
+    owner = getattr(_tls, "owner", None)
+    if owner is None:  # eager launches: scratch is per stream (batches in flight on different streams, pipeline.py)
+        owner, key = _inorm_ws, key + (torch.cuda.current_stream(device).cuda_stream,)
+    ws = owner.get(key)
+    if ws is None:
+        ws = owner[key] = torch.empty(numel, dtype=torch.float64, device=device)
+    return ws
 
 
 def instance_norm_act(x: torch.Tensor, relu: bool = True, residual: Optional[torch.Tensor] = None, eps: float = 1e-5,
@@ -386,11 +413,7 @@ def instance_norm_act(x: torch.Tensor, relu: bool = True, residual: Optional[tor
     require_cuda(x, "x")
     B, H, W, Cc = x.shape
     y = out if out is not None else torch.empty_like(x)
-    key = (str(x.device), B * Cc, torch.cuda.current_stream(x.device).cuda_stream)  # scratch is per stream
-    ws = _inorm_ws.get(key)
-    if ws is None:
-        ws = torch.empty(B * Cc * 3, dtype=torch.float64, device=x.device)  # sums (2 doubles) + scale/shift (2 floats)
-        _inorm_ws[key] = ws
+    ws = _scratch(("inorm", str(x.device), B * Cc), B * Cc * 3, x.device)  # sums (2 doubles) + scale/shift (2 floats)
     if residual is not None:
         require_cuda(residual, "residual")
         assert residual.shape == x.shape
@@ -463,12 +486,7 @@ def first_conv7x7s2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.T
 
 def instance_norm_workspace(x_shape, device) -> torch.Tensor:
     B, _, _, Cc = x_shape
-    key = (str(device), B * Cc, torch.cuda.current_stream(device).cuda_stream)  # scratch is per stream
-    ws = _inorm_ws.get(key)
-    if ws is None:
-        ws = torch.empty(B * Cc * 3, dtype=torch.float64, device=device)  # sums (2 doubles) + scale/shift (2 floats)
-        _inorm_ws[key] = ws
-    return ws
+    return _scratch(("inorm", str(device), B * Cc), B * Cc * 3, device)  # sums (2 doubles) + scale/shift (2 floats)
 
 
 def instance_norm_apply(x: torch.Tensor, ws: torch.Tensor, relu: bool = True, residual: Optional[torch.Tensor] = None, eps: float = 1e-5,
@@ -490,11 +508,7 @@ def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True, r
     require_cuda(x, "x")
     B, H, W, Cc = x.shape
     y = out if out is not None else torch.empty_like(x)
-    key = (str(x.device), "bias", Cc, torch.cuda.current_stream(x.device).cuda_stream)
-    ws = _inorm_ws.get(key)
-    if ws is None:
-        ws = torch.empty(Cc, dtype=torch.float64, device=x.device)
-        _inorm_ws[key] = ws
+    ws = _scratch(("bias", str(x.device), Cc), Cc, x.device)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cc and bias.is_cuda
     with torch.cuda.device(x.device):

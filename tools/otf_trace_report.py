@@ -4,9 +4,11 @@
     PFB_OTF_TRACE=gpurun_out/otf_trace.jsonl python tools/time_config4.py ...
     python tools/otf_trace_report.py gpurun_out/otf_trace.jsonl
 
-Slots (csrc/corr_onthefly_umma.cu): 0 item start, 1 region known, 2 number of bands, 3 level written out; per band kb at
-8 + 6 kb: +0 TMA issue of the band, +1 operands landed (MMA thread), +2 accumulator ready (epilogue thread 0), +3 dump
-done, +4 gather done.
+Slots (csrc/corr_onthefly_umma.cu): 0 item start (epilogue), 1 next item's region published, 2 number of bands, 3 level
+written out; per band kb at 8 + 6 kb: +0 the producer starts issuing the band's loads, +1 the issuer has issued the band's
+MMAs, +2 accumulator ready (epilogue thread 0), +3 dump done, +4 gather done.  The roles run decoupled, so "tma" / "mma" are
+issue-to-issue and issue-to-ready spans (they include queueing); "period" is the time between consecutive bands leaving
+the epilogue, the number that bounds the kernel.
 """
 import json
 import statistics as st
@@ -19,7 +21,7 @@ def main():
     for li, rec in enumerate(launches[:4]):
         g = rec["grid"]
         s = rec["stamps"]
-        rows = {k: [] for k in ("region", "tma", "mma", "dump", "gather", "band", "out", "item", "nb")}
+        rows = {k: [] for k in ("region", "tma", "mma", "dump", "gather", "band", "period", "out", "item", "nb")}
         for c in range(g):
             t = s[c * 64:(c + 1) * 64]
             if not t[0] or not t[3]:
@@ -38,10 +40,12 @@ def main():
                 rows["dump"].append(b[3] - b[2])
                 rows["gather"].append(b[4] - b[3])
                 rows["band"].append(b[4] - b[0])
+                if kb > 0:
+                    rows["period"].append(b[4] - last)
                 last = b[4]
             rows["out"].append(t[3] - last)
         print(f"launch {li}: grid {g}, {len(rows['item'])} CTAs traced, clk (median / p90)")
-        for k in ("nb", "region", "tma", "mma", "dump", "gather", "band", "out", "item"):
+        for k in ("nb", "region", "tma", "mma", "dump", "gather", "band", "period", "out", "item"):
             v = sorted(rows[k])
             if v:
                 print(f"  {k:7s} {st.median(v):9.0f} {v[int(0.9 * (len(v) - 1))]:9.0f}   n={len(v)}")
