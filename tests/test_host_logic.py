@@ -346,3 +346,54 @@ def test_tiled_layout_index_formula():
                 tiled[:, ((y >> 2) * tx + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7)] = dense[:, y, x]
         back = ops.untile_level(torch.from_numpy(tiled), h, w).numpy()
         assert np.array_equal(back, dense)
+
+
+def test_capture_gate_readers_share_writer_alone():
+    """``raft._CaptureGate`` (forwards vs CUDA-graph captures): forwards overlap each other, a capture overlaps nothing, and a
+    waiting capture is not starved by new forwards."""
+    import threading
+    import time
+
+    from ptlflow_b200.models.raft.raft import _CaptureGate
+
+    gate = _CaptureGate()
+    lock = threading.Lock()
+    state = {"readers": 0, "writers": 0, "max_readers": 0, "violations": 0}
+    order = []
+
+    def forward(tag, hold):
+        with gate.forward():
+            with lock:
+                state["readers"] += 1
+                state["max_readers"] = max(state["max_readers"], state["readers"])
+                state["violations"] += state["writers"] != 0
+                order.append(("f", tag))
+            time.sleep(hold)
+            with lock:
+                state["readers"] -= 1
+
+    def capture(tag, hold):
+        with gate.capture():
+            with lock:
+                state["writers"] += 1
+                state["violations"] += state["readers"] != 0 or state["writers"] != 1
+                order.append(("c", tag))
+            time.sleep(hold)
+            with lock:
+                state["writers"] -= 1
+
+    ts = [threading.Thread(target=forward, args=(i, 0.15)) for i in range(3)]
+    for t in ts:
+        t.start()
+    time.sleep(0.03)
+    tc = threading.Thread(target=capture, args=("c0", 0.05))
+    tc.start()  # waits for the three forwards
+    time.sleep(0.03)
+    late = threading.Thread(target=forward, args=("late", 0.0))
+    late.start()  # arrives while the capture is waiting: must queue behind it
+    for t in ts + [tc, late]:
+        t.join(5)
+        assert not t.is_alive()
+    assert state["violations"] == 0
+    assert state["max_readers"] == 3
+    assert order.index(("c", "c0")) < order.index(("f", "late"))
