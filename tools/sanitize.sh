@@ -15,6 +15,16 @@ run() { # tool, selection
   rc=$?
   if [ $rc -eq 0 ]; then echo "SANITIZER $1 [$2]: CLEAN"; elif [ $rc -eq 124 ]; then echo "SANITIZER $1 [$2]: TIME-BOXED (no error before the cut-off)"; else echo "SANITIZER $1 [$2]: FAILED rc=$rc"; fi
 }
+# round-2 kernels: tiled volume / lookup, on-the-fly correlation on the tensor cores (tests/test_gpu_corr_block.py; the 1020-item case is too long under the tool)
+run2() {
+  timeout "$T" compute-sanitizer --tool "$1" --error-exitcode 1 --launch-timeout 120 \
+    python -m pytest tests/test_gpu_corr_block.py -m gpu -x -q -k "(onthefly_tensor_core or tiled) and not 135"
+  rc=$?
+  if [ $rc -eq 0 ]; then echo "SANITIZER $1 [round-2 corr kernels]: CLEAN"; elif [ $rc -eq 124 ]; then echo "SANITIZER $1 [round-2 corr kernels]: TIME-BOXED (no error before the cut-off)"; else echo "SANITIZER $1 [round-2 corr kernels]: FAILED rc=$rc"; fi
+}
+if [ "${PFB_SANITIZE_ONLY_R2:-0}" = "1" ]; then run2 memcheck; run2 synccheck; exit 0; fi
+run2 memcheck
+run2 synccheck
 run memcheck "$UMMA"
 run synccheck "$UMMA"
 run racecheck "$SIMT"
