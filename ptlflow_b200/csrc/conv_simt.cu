@@ -37,19 +37,32 @@ __device__ __forceinline__ float load_src(const SrcDev& s, size_t pix, int c) {
   return to_f32(reinterpret_cast<const T*>(s.ptr)[i]);
 }
 
-template <typename T>
+// Position of a K chunk: (tap, source, first channel).  The K loop walks taps outermost, then the concatenated sources,
+// then 32-channel chunks -- the order of the weight rows ((tap * Cin_total + channel) * Cout_pad).
+struct KPos {
+  int tap, s, c0, cbase;  // cbase = weight row of channel 0 of source s at this tap
+};
+
+// BM x 64 output tile per CTA (BM = 64 / 32 / 16 pixels: the smaller tiles are for small images, where 64-pixel tiles
+// leave most SMs without a CTA), 32-deep K chunks.  The next chunk's operands are fetched into registers while the current
+// one is multiplied out of shared memory (double-buffered, one barrier per chunk): the first version loaded, synchronised,
+// multiplied and synchronised again per 16-deep chunk, i.e. it paid the global-memory latency K / 16 times in sequence --
+// 97 us per layer at raft_small's 16 x 32 grid (BASELINE config 1), whatever the number of CTAs.  The accumulation order
+// along K is unchanged (ascending, one fma per element), so results are bit-identical to that version.
+template <typename T, int BM>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvDev a) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  constexpr int BN = 64, BK = 32;
+  constexpr int MI = BM / 16;           // output pixels per thread (x 4 output channels)
+  constexpr int AV = BM * BK / 256;     // A values per thread and chunk: 8 / 4 / 2 consecutive channels of one pixel
+  constexpr int TPP = BK / AV;          // threads per pixel in the A loader
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int P = a.B * a.H * a.W;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  // A loader: pixel ml, 4 consecutive channels starting at kq
-  const int ml = tid >> 2, kq = (tid & 3) * 4;
-  // B loader: k row kb, 4 consecutive output channels starting at nq
-  const int kb = tid >> 4, nq = (tid & 15) * 4;
+  const int ml = tid / TPP, kq = (tid % TPP) * AV;   // A loader: pixel ml, AV consecutive channels starting at kq
+  const int kb = tid >> 4, nq = (tid & 15) * 4;       // B loader: k rows kb and kb + 16, 4 consecutive output channels at nq
   const int pl = m0 + ml;
   int lb = 0, ly = 0, lx = 0;
   const bool pvalid = pl < P;
@@ -60,56 +73,95 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvDev a) {
     lb = t / a.H;
   }
   const int ph = a.KH / 2, pw = a.KW / 2;
+  const int ntaps = a.KH * a.KW;
   const T* wgt = reinterpret_cast<const T*>(a.weight);
-  float acc[4][4] = {};
-  for (int tap = 0; tap < a.KH * a.KW; ++tap) {
-    const int ky = tap / a.KW, kx = tap - ky * a.KW;
+  float acc[MI][4] = {};
+  float ra[AV], rb[8];
+
+  auto fetch = [&](const KPos& k) {  // global -> registers (no use of the values here: the loads stay in flight)
+    const int ky = k.tap / a.KW, kx = k.tap - ky * a.KW;
     const int iy = ly + ky - ph, ix = lx + kx - pw;
     const bool inb = pvalid && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
     const size_t ipix = ((size_t)lb * a.H + (inb ? iy : 0)) * a.W + (inb ? ix : 0);
-    int cbase = tap * a.Cin_total;
-    for (int s = 0; s < a.nsrc; ++s) {
-      const SrcDev& src = a.src[s];
-      for (int c0 = 0; c0 < src.channels; c0 += BK) {
+    const SrcDev& src = a.src[k.s];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int c = c0 + kq + j;
-          As[kq + j][ml] = (inb && c < src.channels) ? load_src<T>(src, ipix, c) : 0.f;
-        }
-        {
-          int c = c0 + kb;
-          const bool kval = c < src.channels;
-          const T* wrow = wgt + (size_t)(cbase + c) * a.Cout_pad;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            int n = n0 + nq + j;
-            Bs[kb][nq + j] = (kval && n < a.Cout_pad) ? to_f32(wrow[n]) : 0.f;
-          }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-          float av[4], bv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-      }
-      cbase += src.channels;
+    for (int j = 0; j < AV; ++j) {
+      const int c = k.c0 + kq + j;
+      ra[j] = (inb && c < src.channels) ? load_src<T>(src, ipix, c) : 0.f;
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = k.c0 + kb + 16 * h;
+      const bool kval = c < src.channels;
+      const T* wrow = wgt + (size_t)(k.cbase + (kval ? c : 0)) * a.Cout_pad;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + nq + j;
+        rb[4 * h + j] = (kval && n < a.Cout_pad) ? to_f32(wrow[n]) : 0.f;
+      }
+    }
+  };
+  auto stash = [&](int buf) {  // registers -> shared memory
+#pragma unroll
+    for (int j = 0; j < AV; ++j) As[buf][kq + j][ml] = ra[j];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      *reinterpret_cast<float4*>(&Bs[buf][kb + 16 * h][nq]) = make_float4(rb[4 * h], rb[4 * h + 1], rb[4 * h + 2], rb[4 * h + 3]);
+  };
+  auto advance = [&](KPos& k) -> bool {  // next chunk; false after the last one
+    k.c0 += BK;
+    if (k.c0 >= a.src[k.s].channels) {
+      k.c0 = 0;
+      k.cbase += a.src[k.s].channels;
+      if (++k.s == a.nsrc) {
+        k.s = 0;
+        ++k.tap;  // cbase has advanced by Cin_total = the next tap's first row
+      }
+    }
+    return k.tap < ntaps;
+  };
+
+  KPos k{0, 0, 0, 0};
+  fetch(k);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  bool more = advance(k);
+  while (true) {
+    if (more) fetch(k);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[MI];
+      if (MI == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+        av[0] = v.x; av[1 % MI] = v.y; av[2 % MI] = v.z; av[3 % MI] = v.w;
+      } else if (MI == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(&As[buf][kk][ty * 2]);
+        av[0] = v.x; av[1 % MI] = v.y;
+      } else {
+        av[0] = As[buf][kk][ty];
+      }
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        acc[i][0] = fmaf(av[i], bv.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], bv.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], bv.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], bv.w, acc[i][3]);
+      }
+    }
+    if (!more) break;
+    stash(buf ^ 1);  // the other buffer was last read before the previous barrier
+    __syncthreads();
+    buf ^= 1;
+    more = advance(k);
   }
 
   // ---- epilogue --------------------------------------------------------------------------
   const int hd = a.hidden;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int p = m0 + ty * 4 + i;
+  for (int i = 0; i < MI; ++i) {
+    const int p = m0 + ty * MI + i;
     if (p >= P) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -187,10 +239,15 @@ int conv2d_simt(const pfb_conv_params* p, cudaStream_t s) {
   a.out = p->out; a.out_stride = p->out_stride; a.out_offset = p->out_offset;
   a.aux_h = p->aux_h; a.aux_z = p->aux_z; a.hidden = p->hidden; a.coords = p->coords; a.flow = p->flow;
   const int P = p->B * p->H * p->W;
-  dim3 grid(ceil_div(P, 64), ceil_div(p->Cout, 64));
+  // small images: smaller pixel tiles until the grid covers the machine (each CTA's K loop is a latency chain)
+  const int n_tiles = ceil_div(p->Cout, 64), sms = sm_count();
+  const int bm = ceil_div(P, 64) * n_tiles >= sms ? 64 : (ceil_div(P, 32) * n_tiles >= sms ? 32 : 16);
+  dim3 grid(ceil_div(P, bm), n_tiles);
   {
     ProfScope prof(KC_CONV, s);
-    PFB_DISPATCH_DTYPE(p->dtype, T, { conv_simt_kernel<T><<<grid, 256, 0, s>>>(a); });
+    if (bm == 64) PFB_DISPATCH_DTYPE(p->dtype, T, { conv_simt_kernel<T, 64><<<grid, 256, 0, s>>>(a); });
+    else if (bm == 32) PFB_DISPATCH_DTYPE(p->dtype, T, { conv_simt_kernel<T, 32><<<grid, 256, 0, s>>>(a); });
+    else PFB_DISPATCH_DTYPE(p->dtype, T, { conv_simt_kernel<T, 16><<<grid, 256, 0, s>>>(a); });
   }
   PFB_LAUNCH_CHECK();
   return PFB_OK;
