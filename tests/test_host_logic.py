@@ -397,3 +397,85 @@ def test_capture_gate_readers_share_writer_alone():
     assert state["violations"] == 0
     assert state["max_readers"] == 3
     assert order.index(("c", "c0")) < order.index(("f", "late"))
+
+
+def test_onthefly_region_gemm_is_the_lookup():
+    """CPU emulation of csrc/corr_onthefly_umma.cu's algorithm (no GPU): per (8 x 16 query tile, level) ONE region of the level's
+    feature map -- anchored at the smallest window origin, 32 targets wide, bands of 8 rows at stride 7 -- multiplied with the
+    tile's query vectors, and every query's 9 x 9 window blended out of its own row of that product.  Pins, against the oracle's
+    a4 (oracle/raft_oracle.py::alt_corr_lookup), the geometry the kernel relies on: every (window row, tap pair) lies in exactly
+    one band, windows that fit the region need no other data, zero fill outside the map is the sampler's zero padding, the
+    x-major channel order, and which queries are outliers (recomputed by the SIMT kernel on the GPU)."""
+    R, D, K, RW = 4, 10, 9, 32
+    b, c, h, w, levels = 1, 32, 19, 37, 3
+    g = torch.Generator().manual_seed(5)
+    f1 = torch.randn(b, c, h, w, generator=g)
+    f2 = torch.randn(b, c, h, w, generator=g)
+    coords = O.coords_grid(b, h, w) + torch.tensor([2.3, -1.6]).view(1, 2, 1, 1) + 1.2 * torch.randn(b, 2, h, w, generator=g)
+    coords[0, :, 3, 5] = torch.tensor([-40.0, 7.0])      # window entirely outside: zeros, not an outlier
+    coords[0, :, 10, 20] = torch.tensor([-3.0, 9.0])     # far left of its tile's other windows: it becomes the anchor, the
+                                                         # windows more than 22 columns to its right do not fit the region
+    ref = O.alt_corr_lookup(f1, f2, coords, R, levels)   # [b, levels*81, h, w]
+    scale = 1.0 / np.sqrt(c)
+
+    pyr, f = [], f2
+    for lvl in range(levels):
+        if lvl:
+            f = torch.nn.functional.avg_pool2d(f, 2, stride=2)
+        pyr.append(f[0].permute(1, 2, 0).numpy())       # [Hl, Wl, C]
+    q1 = f1[0].permute(1, 2, 0).numpy()
+    cx, cy = coords[0, 0].numpy(), coords[0, 1].numpy()
+    out = np.zeros((h, w, levels * K * K), np.float32)
+    served = np.zeros((h, w, levels), bool)
+    outliers = 0
+    for ty in range(0, h, 8):
+        for tx in range(0, w, 16):
+            ys, xs = np.meshgrid(np.arange(ty, min(ty + 8, h)), np.arange(tx, min(tx + 16, w)), indexing="ij")
+            ys, xs = ys.ravel(), xs.ravel()
+            for lvl in range(levels):
+                Hl, Wl, _ = pyr[lvl].shape
+                x, y = cx[ys, xs] / 2**lvl, cy[ys, xs] / 2**lvl
+                xf, yf = np.floor(x), np.floor(y)
+                fx, fy = (x - xf).astype(np.float32), (y - yf).astype(np.float32)
+                x0, y0 = xf.astype(int) - R, yf.astype(int) - R
+                live = (x0 + D - 1 >= 0) & (x0 < Wl) & (y0 + D - 1 >= 0) & (y0 < Hl)
+                served[ys[~live], xs[~live], lvl] = True  # all-zero windows
+                if not live.any():
+                    continue
+                bx0, by0, By = x0[live].min(), y0[live].min(), y0[live].max()
+                nb = min(max((By + D - 1 - by0 + 6) // 7, 1), 8)
+                # the region, zero outside the map (what the TMA unit fills in)
+                reg = np.zeros((7 * nb + 1, RW, c), np.float32)
+                for ry in range(reg.shape[0]):
+                    for rx in range(RW):
+                        yy, xx = by0 + ry, bx0 + rx
+                        if 0 <= yy < Hl and 0 <= xx < Wl:
+                            reg[ry, rx] = pyr[lvl][yy, xx]
+                for qi in np.nonzero(live)[0]:
+                    cxo, ryo = x0[qi] - bx0, y0[qi] - by0
+                    if cxo + D > RW or ryo + D - 1 > 7 * nb:
+                        outliers += 1
+                        continue
+                    qv = q1[ys[qi], xs[qi]]
+                    w00, w10 = (1 - fx[qi]) * (1 - fy[qi]) * scale, fx[qi] * (1 - fy[qi]) * scale
+                    w01, w11 = (1 - fx[qi]) * fy[qi] * scale, fx[qi] * fy[qi] * scale
+                    hits = np.zeros(K, int)
+                    for kb in range(nb):
+                        band = reg[7 * kb: 7 * kb + 8].reshape(-1, c) @ qv   # this query's accumulator row of the band GEMM
+                        for j in range(K):
+                            rr = ryo + j - 7 * kb
+                            if rr < 0 or rr > 6:
+                                continue
+                            hits[j] += 1
+                            up, dn = band[rr * RW + cxo: rr * RW + cxo + D], band[(rr + 1) * RW + cxo: (rr + 1) * RW + cxo + D]
+                            for i in range(K):
+                                out[ys[qi], xs[qi], lvl * K * K + i * K + j] = w00 * up[i] + w10 * up[i + 1] + w01 * dn[i] + w11 * dn[i + 1]
+                    assert (hits == 1).all(), "every window row is served by exactly one band"
+                    served[ys[qi], xs[qi], lvl] = True
+    assert outliers >= 1 and served[10, 20].all() and not served[8:16, 16:32].all()
+    refp = ref[0].permute(1, 2, 0).numpy().reshape(h, w, levels, K * K)
+    got = out.reshape(h, w, levels, K * K)
+    assert served.mean() > 0.7
+    err = np.abs(got - refp)[served].max()
+    assert err < 2e-4, err
+    assert np.abs(got[3, 5]).max() == 0 and np.abs(refp[3, 5]).max() == 0
