@@ -479,3 +479,31 @@ def test_onthefly_region_gemm_is_the_lookup():
     err = np.abs(got - refp)[served].max()
     assert err < 2e-4, err
     assert np.abs(got[3, 5]).max() == 0 and np.abs(refp[3, 5]).max() == 0
+
+
+@pytest.mark.parametrize("radius", [3, 4])
+def test_tiled_lookup_blend_lane_map_covers_the_window(radius):
+    """The lane -> window position map of corr_lookup_tiled_kernel's blend phase (csrc/corr_tiled.cu: rounds of 8 rows x 4 columns,
+    plus one mixed round for the ninth row / column of a 9 x 9 window): every position exactly once, and within a round the
+    staged rows a warp reads are 12 words apart with at most 3 words per row -- no two lanes on one bank unless on one word."""
+    K = 2 * radius + 1
+    npos = 3 if K == 9 else (K + 3) // 4
+    seen = {}
+    for k in range(npos):
+        banks = {}
+        for lane in range(32):
+            if K == 9 and k == 2:
+                i, j, act = (8, lane, lane < 17) if lane < 8 else (lane - 8, 8, lane < 17)
+            else:
+                i, j = (lane >> 3) + 4 * k, lane & 7
+                act = j < K and i < K
+            if not act:
+                continue
+            assert (i, j) not in seen
+            seen[(i, j)] = (k, lane)
+            for off in (0, 7):  # window origin inside its 8-column tile: the two extremes
+                word = (j * 24 + i + off) // 2
+                banks.setdefault((off, word % 32), set()).add(word)
+        if not (K == 9 and k == 2):
+            assert all(len(v) == 1 for v in banks.values()), f"round {k}: two different words on one bank"
+    assert len(seen) == K * K
