@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ... import ops
+from ... import _lib, ops
 
 
 def _norm(kind: str, channels: int, groups: int = 8) -> nn.Module:
@@ -85,10 +85,15 @@ def _fold(conv: nn.Conv2d, norm: nn.Module, dtype, device):
         t = norm.bias.detach().float().to(device) - norm.running_mean.detach().float().to(device) * s
         w = w * s.view(-1, 1, 1, 1)
         b = b * s + t
-    return w.to(dtype).contiguous(memory_format=torch.channels_last), b.contiguous()  # bias stays fp32: added by our kernels
+    w = w.to(dtype).contiguous(memory_format=torch.channels_last)
+    b = b.contiguous()  # fp32: added by this library's kernels
+    if dtype == torch.float32:
+        return w, b
+    return w, b, b.to(dtype)  # + the storage-type copy cuDNN's fused bias + ReLU epilogue wants (cast once, not per forward)
 
 
 _NATIVE_CONV1 = bool(int(os.environ.get("PFB_NATIVE_CONV1", "1")))
+_NATIVE_CONV2 = bool(int(os.environ.get("PFB_NATIVE_CONV2", "1")))
 # batch-norm-folded convolutions without a residual join: cuDNN's own conv + bias + ReLU epilogue instead of a separate pass
 _CUDNN_FUSED_RELU = bool(int(os.environ.get("PFB_CUDNN_FUSED_RELU", "1")))
 _prep_lock = threading.Lock()
@@ -160,6 +165,13 @@ class _Encoder(nn.Module):
                 and self.norm_fn in ("instance", "batch", "none")):
             folded = _fold(self.conv1, self.norm1, torch.float32, device)
             prep["conv1_native"] = (ops.pack_first_conv(folded[0], dtype), folded[1])
+        # the output projection (1x1, w3 -> output_dim) on this library's tcgen05 implicit-GEMM kernel with the bias in its
+        # epilogue: cuDNN picked an sm_80 kernel without shared-memory staging for it (50 us per encoder, ncu launch list r02f)
+        # and the bias needed a pass of its own
+        c2 = self.conv2
+        if (_NATIVE_CONV2 and dtype in (torch.float16, torch.bfloat16) and tuple(c2.kernel_size) == (1, 1) and c2.in_channels % 64 == 0
+                and c2.out_channels % 32 == 0 and c2.out_channels <= 1024):
+            prep["conv2_native"] = ops.PackedConv([c2], dtype, device, src_channels=[c2.in_channels])
         # the fold / pack kernels ran on this thread's stream: finish them before other streams can see the cache
         torch.cuda.current_stream(device).synchronize()
         self._prep_cache = (sig, prep)
@@ -217,6 +229,10 @@ class _Encoder(nn.Module):
             else:  # residual: 3x3 (stride) -> 3x3
                 y = conv_act(x, e["conv1"], s, 1)
                 x = conv_act(y, e["conv2"], 1, 1, relu=True, residual=xs)
+        if "conv2_native" in prep and x.is_contiguous():
+            packed = prep["conv2_native"]
+            out = torch.empty(x.shape[:3] + (packed.Cout,), dtype=x.dtype, device=x.device)
+            return ops.conv2d([x], packed, out, epilogue=_lib.EPI_LINEAR)
         y = _conv_pm(x, prep["conv2"], 1, 0)
         return ops.bias_act(y, prep["conv2"][1], relu=False, out=y)
 
