@@ -455,6 +455,9 @@ def run_ours(args):
         prof_steps = 2
         was_graph = model.use_cuda_graph
         model.use_cuda_graph = False
+        # one stream, no fork / join: a kernel's span must not contain a kernel of another class running beside it
+        was_fork = (getattr(model, "fork_flow", False), getattr(model, "fork_encoders", False))
+        model.fork_flow = model.fork_encoders = False
         step_resident(0)
         torch.cuda.synchronize()
         lib.pfb_profile_enable(1)
@@ -468,6 +471,7 @@ def run_ours(args):
         lib.pfb_profile_enable(0)
         ms_prof_step = t_ev0.elapsed_time(t_ev1) / prof_steps
         model.use_cuda_graph = was_graph
+        model.fork_flow, model.fork_encoders = was_fork
         log("instrumented pass done")
         if pipe is not None:
             pipe.close()
@@ -542,7 +546,7 @@ def run_ours(args):
         "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype] + " storage, f32 accumulate/coordinates",
         "data": "synthetic (torch.rand frames, random-init weights, seed 1234)",
         "config": {"workload": f"{args.model} {W}x{H} {args.iters} iters, batch {B} per GPU (BASELINE.json configs[1])",
-                   "pairs_per_step_per_gpu": B, "batches_in_flight_per_gpu": args.inflight, "cuda_graph": bool(model.use_cuda_graph), "alternate_corr": bool(args.alternate_corr),
+                   "pairs_per_step_per_gpu": B, "batches_in_flight_per_gpu": args.inflight, "stream_forks": {"flow_branch": bool(getattr(model, "fork_flow", False)), "encoders": bool(getattr(model, "fork_encoders", False))}, "cuda_graph": bool(model.use_cuda_graph), "alternate_corr": bool(args.alternate_corr),
                    "fp32_context": bool(args.fp32_context), "value_remeasured": value_remeasured, "e2e_remeasured": e2e_remeasured,
                    "parallelism": f"replicas x{world}, frame pairs sharded, no data-path collective",
                    "l2": "per-step working set (>= 1 GB correlation pyramid at batch 8) exceeds the 126 MB L2; inputs rotate over a pool of 3 batches",

@@ -310,6 +310,9 @@ typedef struct {
   int out_h, out_w, pad_top, pad_left; /* full-resolution output window */
   int impl;           /* 0 auto, 1 SIMT everywhere, 2 tcgen05 where available */
   int volume_layout;  /* 0: dense pyramid (pfb_corr_volume_build); 1: tiled pyramid (pfb_corr_volume_build_tiled) */
+  int fork_flow;      /* 1: the flow branch of the motion encoder (convf1, convf2) and the once-per-forward context terms run on a second
+                         stream of the calling host thread, forked / joined with events (parallel branches when the caller captures a
+                         CUDA graph); 0: everything on `stream`.  Half-precision tensor path only, ignored elsewhere. */
 } pfb_raft_cfg;
 
 typedef struct {

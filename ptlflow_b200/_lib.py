@@ -61,7 +61,7 @@ class RaftCfg(C.Structure):
         ("feat_dim", C.c_int), ("corr_levels", C.c_int), ("corr_radius", C.c_int),
         ("hidden_dim", C.c_int), ("context_dim", C.c_int), ("iters", C.c_int), ("alternate_corr", C.c_int),
         ("out_h", C.c_int), ("out_w", C.c_int), ("pad_top", C.c_int), ("pad_left", C.c_int), ("impl", C.c_int),
-        ("volume_layout", C.c_int),
+        ("volume_layout", C.c_int), ("fork_flow", C.c_int),
     ]
 
 
@@ -174,22 +174,44 @@ def stream_ptr(device=None) -> int:
 
 _private_streams: dict = {}
 _private_lock = threading.Lock()
+_private_tls = threading.local()
+
+
+def _new_private_stream(idx: int) -> "torch.cuda.Stream":
+    raw = C.c_void_p()
+    with torch.cuda.device(idx):
+        check(load().pfb_stream_create(C.byref(raw)), "stream_create")
+    return torch.cuda.ExternalStream(raw.value, device=torch.device("cuda", idx))
+
+
+def _device_index(device) -> int:
+    dev = torch.device(device)
+    return dev.index if dev.index is not None else torch.cuda.current_device()
 
 
 def private_stream(device) -> "torch.cuda.Stream":
     """One stream per device that no other code can be handed: ``torch.cuda.Stream()`` draws from a pool of 32 and two
     callers can hold the same underlying stream (a pipeline slot launching eagerly on the stream another thread is capturing
     puts its kernels into that capture and fails its own allocations).  CUDA-graph captures run here, one at a time."""
-    dev = torch.device(device)
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    idx = _device_index(device)
     with _private_lock:
         st = _private_streams.get(idx)
         if st is None:
-            raw = C.c_void_p()
-            with torch.cuda.device(idx):
-                check(load().pfb_stream_create(C.byref(raw)), "stream_create")
-            st = _private_streams[idx] = torch.cuda.ExternalStream(raw.value, device=torch.device("cuda", idx))
+            st = _private_streams[idx] = _new_private_stream(idx)
         return st
+
+
+def thread_stream(device, tag: str = "aux") -> "torch.cuda.Stream":
+    """A private stream of THIS host thread (and device): the second lane of a forward's fork / join sections (the two
+    encoders side by side).  Forwards of different host threads run concurrently, so each brings its own."""
+    idx = _device_index(device)
+    streams = getattr(_private_tls, "streams", None)
+    if streams is None:
+        streams = _private_tls.streams = {}
+    st = streams.get((idx, tag))
+    if st is None:
+        st = streams[(idx, tag)] = _new_private_stream(idx)
+    return st
 
 
 def require_cuda(t: torch.Tensor, name: str) -> None:

@@ -97,6 +97,9 @@ struct Ctx {
   Workspace ws;
   char* base;
   cudaStream_t s;
+  // flow branch of the motion encoder on a second stream (fork_flow_branch): null when not forked
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   void* at(size_t off) const { return base + off; }
 };
 
@@ -141,6 +144,24 @@ static bool merged_c2f2_active(const Ctx& x) {
   static const int env = getenv("PFB_MERGE_C2F2") ? atoi(getenv("PFB_MERGE_C2F2")) : 0;
   return env && tensor_path(x) && x.w->layers[PFB_L_CONVC2F2].weight_k;
 }
+// The motion encoder has two independent branches: lookup -> convc1 -> convc2 (correlation) and convf1 -> convf2 (flow); both
+// start from the previous iteration's coordinates and meet in `conv`.  cfg.fork_flow puts the flow branch on a second stream
+// of this host thread (fork / join with events, which a CUDA-graph capture turns into parallel branches of the graph), so that
+// the SIMT lookup can share the SMs with the two small tensor-core layers (+0.3 ... 2 % per step).
+static bool fork_flow_active(const Ctx& x) { return x.c->fork_flow && tensor_path(x) && !merged_c2f2_active(x); }
+static int fork_flow_setup(Ctx& x) {
+  if (!fork_flow_active(x)) return PFB_OK;
+  thread_local cudaStream_t side = nullptr;
+  thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!side) {
+    PFB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    PFB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    PFB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  x.side = side; x.ev_fork = ev_fork; x.ev_join = ev_join;
+  return PFB_OK;
+}
+
 // conv_inp(inp) + bias for the four GRU convolutions: once per forward (inp does not change over the iterations)
 static int run_context_terms(const Ctx& x) {
   if (!ctx_split_active(x)) return PFB_OK;
@@ -188,6 +209,8 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
 
   // ---- motion encoder (update.py:76-112) ----
   const bool merged_c2f2 = merged_c2f2_active(x);
+  Ctx xf = x;  // the flow branch's launches: the side stream when forked (the fork itself is in the caller, before the lookup)
+  if (x.side) xf.s = x.side;
   if (c->variant != 1) {
     void* cor1 = x.at(ws.off_cor1);
     PFB_TRY(run_conv(x, PFB_L_CONVC1, {src_of(corr, ws.planes, corr_stride)}, PFB_EPI_RELU, cor1, ws.c_cor1, 0));
@@ -199,15 +222,19 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
     const pfb_layer& LF = x.w->layers[PFB_L_CONVF1];
     static const int env_fc = getenv("PFB_FLOW_CONV_UMMA") ? atoi(getenv("PFB_FLOW_CONV_UMMA")) : 1;
     if (env_fc && LF.weight_k && LF.KH == 7 && LF.KW == 7 && LF.Cin == 2 && LF.Cout == 128 && c->dtype != PFB_F32 && c->impl != 1)
-      PFB_TRY(pfb_flow_conv7x7(flow, LF.weight_k, LF.bias, flo1, ws.c_flo1, 0, c->B, c->H, c->W, c->dtype, (pfb_stream)x.s));
+      PFB_TRY(pfb_flow_conv7x7(flow, LF.weight_k, LF.bias, flo1, ws.c_flo1, 0, c->B, c->H, c->W, c->dtype, (pfb_stream)xf.s));
     else
-      PFB_TRY(run_conv(x, PFB_L_CONVF1, {src_of(flow, 2, 2, 0, 1)}, PFB_EPI_RELU, flo1, ws.c_flo1, 0));
+      PFB_TRY(run_conv(xf, PFB_L_CONVF1, {src_of(flow, 2, 2, 0, 1)}, PFB_EPI_RELU, flo1, ws.c_flo1, 0));
   }
   if (merged_c2f2)  // convc2 | convf2 as one block-diagonal layer: [cor1 (256) | flo1 (128)] -> [cor (192) | flo (64)]
     PFB_TRY(run_conv(x, PFB_L_CONVC2F2, {src_of(x.at(ws.off_cor1), ws.c_cor1, ws.c_cor1), src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU,
                      corflo, ws.c_corflo, 0));
   else
-    PFB_TRY(run_conv(x, PFB_L_CONVF2, {src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU, corflo, ws.c_corflo, ws.c_cor2));
+    PFB_TRY(run_conv(xf, PFB_L_CONVF2, {src_of(flo1, ws.c_flo1, ws.c_flo1)}, PFB_EPI_RELU, corflo, ws.c_corflo, ws.c_cor2));
+  if (x.side) {  // join: `conv` reads both branches
+    PFB_CUDA(cudaEventRecord(x.ev_join, x.side));
+    PFB_CUDA(cudaStreamWaitEvent(x.s, x.ev_join, 0));
+  }
   PFB_TRY(run_conv(x, PFB_L_CONV, {src_of(corflo, ws.c_corflo, ws.c_corflo)}, PFB_EPI_RELU_APPEND_FLOW, motion, ws.c_motion, 0));
 
   // ---- gma: motion_global = motion + gamma * (attention @ to_v(motion))   gma_utils.py:101-113, gma/update.py:149 ----
@@ -342,8 +369,23 @@ extern "C" PFB_API int pfb_raft_refine(const pfb_raft_cfg* cfg, const pfb_raft_w
   PFB_CHECK_ARG(cfg->variant == 1 || cfg->iters >= 1, "raft_refine: the convex upsample needs at least one iteration (mask)");
   PFB_TRY(launch_flow_from_coords(buf->coords, reinterpret_cast<float*>(x.at(x.ws.off_flow)), cfg->B, cfg->H, cfg->W, x.s));
   void* mask = cfg->variant != 1 ? x.at(x.ws.off_mask) : nullptr;
-  PFB_TRY(run_context_terms(x));
+  PFB_TRY(fork_flow_setup(x));
+  if (x.side) {
+    // the once-per-forward context terms ride the side stream too: they are first read by the GRU of iteration 0, after that
+    // iteration's join (same stream as its flow branch, so the join covers them)
+    PFB_CUDA(cudaEventRecord(x.ev_fork, x.s));
+    PFB_CUDA(cudaStreamWaitEvent(x.side, x.ev_fork, 0));
+    Ctx xs = x;
+    xs.s = x.side;
+    PFB_TRY(run_context_terms(xs));
+  } else {
+    PFB_TRY(run_context_terms(x));
+  }
   for (int it = 0; it < cfg->iters; ++it) {
+    if (x.side) {  // fork: the flow branch may start as soon as the previous iteration's coordinates are written
+      PFB_CUDA(cudaEventRecord(x.ev_fork, x.s));
+      PFB_CUDA(cudaStreamWaitEvent(x.side, x.ev_fork, 0));
+    }
     PFB_TRY(lookup(x));
     PFB_TRY(update_iter(x, nullptr, it == cfg->iters - 1 ? mask : nullptr));
   }

@@ -136,7 +136,7 @@ class RaftEngine:
     def make_cfg(self, B: int, H: int, W: int, iters: int, out_hw, pad, alternate_corr: bool, feat_dim: int, volume_layout: int = 0) -> _lib.RaftCfg:
         return _lib.RaftCfg(self.variant, dtype_code(self.dtype), B, H, W, feat_dim, self.corr_levels, self.corr_radius,
                             self.hidden_dim, self.context_dim, iters, int(alternate_corr), out_hw[0], out_hw[1], pad[0], pad[1],
-                            self.impl, 0 if alternate_corr else int(volume_layout))
+                            self.impl, 0 if alternate_corr else int(volume_layout), int(getattr(self, "fork_flow", False)))
 
     def build_volume(self, fmap1: torch.Tensor, fmap2: torch.Tensor, impl: int = 0):
         """a1 + a2 for the refinement loop of this engine.  f16 / bf16 with tensor-core-shaped features get the tiled

@@ -142,6 +142,11 @@ class RAFT(BaseModel):
         # channels of the pre-processed frames handed to the first convolution (>= 3, extra channels zero): with 3,
         # cuDNN runs its own NHWC channel-padding kernel in front of the 7x7 convolution (ncu launch list r01 v15)
         self.frame_channels = int(_os.environ.get("PFB_FRAME_CHANNELS", "4"))
+        # independent branches of a forward on a second stream (fork / join; parallel branches of the CUDA graph): fnet beside cnet,
+        # and inside the refinement loop the flow branch of the motion encoder beside the lookup / correlation branch
+        self.fork_encoders = bool(int(_os.environ.get("PFB_FORK_ENCODERS", "1")))
+        self.fork_flow = bool(int(_os.environ.get("PFB_FORK_FLOW", "1")))
+        self._enc_tuned: set = set()
         self._engine: Optional[RaftEngine] = None
         # one CUDA graph per (input shape, dtype, iters, stream): PFB_CUDA_GRAPH=0 or model.use_cuda_graph = False -> eager launches
         self.use_cuda_graph = bool(int(_os.environ.get("PFB_CUDA_GRAPH", "1")))
@@ -175,6 +180,7 @@ class RAFT(BaseModel):
                              self.corr_radius, dtype, device, impl=self.kernel_impl, **self._extra_engine_args())
             eng.extra_signature = self._extra_signature()
             self._engine = eng
+        eng.fork_flow = self.fork_flow  # pfb_raft_cfg.fork_flow of the next refine() calls
         return eng
 
     def _extra_engine_args(self) -> Dict:
@@ -200,10 +206,28 @@ class RAFT(BaseModel):
         # (ncu launch list r01_launches_v7); benchmark mode selects per shape once.
         strict = frames.dtype == torch.float32 and self.strict_fp32
         with _cudnn_flags(self.cudnn_benchmark, not strict):
-            fmaps = run(self.fnet, frames)
             cnet32 = self.__dict__.get("_cnet_fp32")
-            if cnet32 is None or frames.dtype == torch.float32:
-                cnet = run(self.cnet, frames[:B])
+            own_cnet = cnet32 is None or frames.dtype == torch.float32
+            tuned_key = (tuple(frames.shape), frames.dtype)
+            tuned = tuned_key in self._enc_tuned  # first sight of a shape runs serially: cuDNN's autotuner times kernels then
+            self._enc_tuned.add(tuned_key)
+            if own_cnet and self.fork_encoders and tuned and frames.dtype != torch.float32:
+                # the two encoders are independent and each alternates tensor-bound convolutions with HBM-bound normalise /
+                # statistics passes: on two streams (fork / join; parallel branches of the CUDA graph) one's convolutions fill
+                # the SMs the other's memory passes leave idle
+                from ... import _lib
+
+                cur = torch.cuda.current_stream(frames.device)
+                aux = _lib.thread_stream(frames.device)
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    cnet = run(self.cnet, frames[:B])
+                fmaps = run(self.fnet, frames)
+                cur.wait_stream(aux)
+            else:
+                fmaps = run(self.fnet, frames)
+                if own_cnet:
+                    cnet = run(self.cnet, frames[:B])
         if cnet32 is not None and frames.dtype != torch.float32:
             # accuracy mode (enable_fp32_context): the context encoder in true fp32, its output rounded once to the storage type
             with _cudnn_flags(self.cudnn_benchmark, False):
@@ -279,7 +303,7 @@ class RAFT(BaseModel):
     def _graph_key(self, images: torch.Tensor, flow_init) -> tuple:
         sid = torch.cuda.current_stream(images.device).cuda_stream  # one graph (and one set of static buffers) per stream
         return (tuple(images.shape), images.dtype, str(images.device), sid, self.iters, bool(self.alternate_corr), flow_init is not None,
-                self.kernel_impl, self.corr_levels, self.corr_radius, self.encoder_chunk, self.frame_channels)
+                self.kernel_impl, self.corr_levels, self.corr_radius, self.encoder_chunk, self.frame_channels, self.fork_encoders, self.fork_flow)
 
     def _weights_signature(self) -> tuple:
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple((b.data_ptr(), b._version) for b in self.buffers())

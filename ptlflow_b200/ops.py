@@ -398,9 +398,12 @@ def scratch_scope(owner: Optional[dict]):
 
 
 def _scratch(key: tuple, numel: int, device) -> torch.Tensor:
+    # per stream in either case: batches in flight on different streams (pipeline.py), the two encoders of one forward on two
+    # streams (RAFT._encode); inside a graph the stream is the capture-time one, which is why the owner matters as well
+    key = key + (torch.cuda.current_stream(device).cuda_stream,)
     owner = getattr(_tls, "owner", None)
-    if owner is None:  # eager launches: scratch is per stream (batches in flight on different streams, pipeline.py)
-        owner, key = _inorm_ws, key + (torch.cuda.current_stream(device).cuda_stream,)
+    if owner is None:
+        owner = _inorm_ws
     ws = owner.get(key)
     if ws is None:
         ws = owner[key] = torch.empty(numel, dtype=torch.float64, device=device)
