@@ -308,6 +308,15 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
   }
 
   // ---- heads (update.py:6-14, :138-152) ----
+  const bool fork_mask = x.side && mask_out && c->variant != 1;
+  if (fork_mask) {  // last iteration: the mask head beside the flow head (both read the final hidden state)
+    PFB_CUDA(cudaEventRecord(x.ev_fork, x.s));
+    PFB_CUDA(cudaStreamWaitEvent(x.side, x.ev_fork, 0));
+    void* mh = x.at(ws.off_mh);
+    PFB_TRY(run_conv(xf, PFB_L_MASK1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, mh, 256, 0));
+    PFB_TRY(run_conv(xf, PFB_L_MASK2, {src_of(mh, 256, 256)}, PFB_EPI_LINEAR, mask_out, 576, 0, 0.25f));
+    PFB_CUDA(cudaEventRecord(x.ev_join, x.side));
+  }
   PFB_TRY(run_conv(x, PFB_L_FLOW1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, fh, ws.c_fh, 0));
   const pfb_layer& LT = x.w->layers[PFB_L_FLOW2T];
   if (c->variant != 1 && c->dtype != PFB_F32 && c->impl != 1 && LT.weight_k) {
@@ -318,7 +327,9 @@ static int update_iter(const Ctx& x, const void* corr_ext, void* mask_out) {
   } else {
     PFB_TRY(run_conv(x, PFB_L_FLOW2, {src_of(fh, ws.c_fh, ws.c_fh)}, PFB_EPI_FLOW, flow, 2, 0));
   }
-  if (mask_out && c->variant != 1) {
+  if (fork_mask) {
+    PFB_CUDA(cudaStreamWaitEvent(x.s, x.ev_join, 0));  // the upsample reads the mask
+  } else if (mask_out && c->variant != 1) {
     void* mh = x.at(ws.off_mh);
     PFB_TRY(run_conv(x, PFB_L_MASK1, {src_of(x.b->net, hd, hd)}, PFB_EPI_RELU, mh, 256, 0));
     PFB_TRY(run_conv(x, PFB_L_MASK2, {src_of(mh, 256, 256)}, PFB_EPI_LINEAR, mask_out, 576, 0, 0.25f));

@@ -146,6 +146,7 @@ class RAFT(BaseModel):
         # and inside the refinement loop the flow branch of the motion encoder beside the lookup / correlation branch
         self.fork_encoders = bool(int(_os.environ.get("PFB_FORK_ENCODERS", "1")))
         self.fork_flow = bool(int(_os.environ.get("PFB_FORK_FLOW", "1")))
+        self.encoder_lanes = int(_os.environ.get("PFB_ENCODER_LANES", "2"))  # 2: fnet | cnet; 3: fnet(frame 1) | fnet(frame 2) | cnet
         self._enc_tuned: set = set()
         self._engine: Optional[RaftEngine] = None
         # one CUDA graph per (input shape, dtype, iters, stream): PFB_CUDA_GRAPH=0 or model.use_cuda_graph = False -> eager launches
@@ -211,28 +212,45 @@ class RAFT(BaseModel):
             tuned_key = (tuple(frames.shape), frames.dtype)
             tuned = tuned_key in self._enc_tuned  # first sight of a shape runs serially: cuDNN's autotuner times kernels then
             self._enc_tuned.add(tuned_key)
-            if own_cnet and self.fork_encoders and tuned and frames.dtype != torch.float32:
-                # the two encoders are independent and each alternates tensor-bound convolutions with HBM-bound normalise /
-                # statistics passes: on two streams (fork / join; parallel branches of the CUDA graph) one's convolutions fill
-                # the SMs the other's memory passes leave idle
+            half = frames.dtype != torch.float32
+            lanes = self.encoder_lanes if (self.fork_encoders and half) else 1
+            split_fnet = lanes >= 3  # instance norm is per sample, so fnet on the two frames of the pairs separately is exact
+            fmap1 = fmap2 = None
+            if lanes >= 2 and tuned and own_cnet:
+                # fnet (one or two lanes) and cnet are independent, and each alternates tensor-bound convolutions with HBM-bound
+                # normalise / statistics passes: on separate streams (fork / join; parallel branches of the CUDA graph) one
+                # lane's convolutions fill the SMs another's memory passes leave idle
                 from ... import _lib
 
                 cur = torch.cuda.current_stream(frames.device)
-                aux = _lib.thread_stream(frames.device)
+                aux = _lib.thread_stream(frames.device, "aux")
                 aux.wait_stream(cur)
                 with torch.cuda.stream(aux):
                     cnet = run(self.cnet, frames[:B])
-                fmaps = run(self.fnet, frames)
+                if split_fnet:
+                    aux2 = _lib.thread_stream(frames.device, "aux2")
+                    aux2.wait_stream(cur)
+                    with torch.cuda.stream(aux2):
+                        fmap1 = run(self.fnet, frames[:B])
+                    fmap2 = run(self.fnet, frames[B:])
+                    cur.wait_stream(aux2)
+                else:
+                    fmaps = run(self.fnet, frames)
                 cur.wait_stream(aux)
             else:
-                fmaps = run(self.fnet, frames)
+                if split_fnet:
+                    fmap1, fmap2 = run(self.fnet, frames[:B]), run(self.fnet, frames[B:])
+                else:
+                    fmaps = run(self.fnet, frames)
                 if own_cnet:
                     cnet = run(self.cnet, frames[:B])
+            if fmap1 is None:
+                fmap1, fmap2 = fmaps[:B], fmaps[B:]
         if cnet32 is not None and frames.dtype != torch.float32:
             # accuracy mode (enable_fp32_context): the context encoder in true fp32, its output rounded once to the storage type
             with _cudnn_flags(self.cudnn_benchmark, False):
                 cnet = run(cnet32, frames[:B].float()).to(frames.dtype)
-        return fmaps[:B], fmaps[B:], cnet
+        return fmap1, fmap2, cnet
 
     def enable_fp32_context(self, on: bool = True) -> "RAFT":
         """Accuracy mode for f16 / bf16 models: evaluate the context encoder in true fp32 (weights as they are NOW, so call
@@ -303,7 +321,7 @@ class RAFT(BaseModel):
     def _graph_key(self, images: torch.Tensor, flow_init) -> tuple:
         sid = torch.cuda.current_stream(images.device).cuda_stream  # one graph (and one set of static buffers) per stream
         return (tuple(images.shape), images.dtype, str(images.device), sid, self.iters, bool(self.alternate_corr), flow_init is not None,
-                self.kernel_impl, self.corr_levels, self.corr_radius, self.encoder_chunk, self.frame_channels, self.fork_encoders, self.fork_flow)
+                self.kernel_impl, self.corr_levels, self.corr_radius, self.encoder_chunk, self.frame_channels, self.fork_encoders, self.fork_flow, self.encoder_lanes)
 
     def _weights_signature(self) -> tuple:
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple((b.data_ptr(), b._version) for b in self.buffers())
