@@ -151,14 +151,23 @@ static bool merged_c2f2_active(const Ctx& x) {
 static bool fork_flow_active(const Ctx& x) { return x.c->fork_flow && tensor_path(x) && !merged_c2f2_active(x); }
 static int fork_flow_setup(Ctx& x) {
   if (!fork_flow_active(x)) return PFB_OK;
-  thread_local cudaStream_t side = nullptr;
-  thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  if (!side) {
-    PFB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    PFB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    PFB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  // one side stream + event pair per (host thread, device): forwards of different host threads run concurrently
+  struct Lane {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  };
+  constexpr int kMaxDev = 64;
+  thread_local Lane lanes[kMaxDev];
+  int dev = 0;
+  PFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) return PFB_OK;  // no fork on exotic device numbers: everything stays on the caller's stream
+  Lane& l = lanes[dev];
+  if (!l.side) {
+    PFB_CUDA(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
+    PFB_CUDA(cudaEventCreateWithFlags(&l.ev_fork, cudaEventDisableTiming));
+    PFB_CUDA(cudaEventCreateWithFlags(&l.ev_join, cudaEventDisableTiming));
   }
-  x.side = side; x.ev_fork = ev_fork; x.ev_join = ev_join;
+  x.side = l.side; x.ev_fork = l.ev_fork; x.ev_join = l.ev_join;
   return PFB_OK;
 }
 
