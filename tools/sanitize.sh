@@ -23,6 +23,7 @@ run2() {
   if [ $rc -eq 0 ]; then echo "SANITIZER $1 [round-2 corr kernels]: CLEAN"; elif [ $rc -eq 124 ]; then echo "SANITIZER $1 [round-2 corr kernels]: TIME-BOXED (no error before the cut-off)"; else echo "SANITIZER $1 [round-2 corr kernels]: FAILED rc=$rc"; fi
 }
 if [ "${PFB_SANITIZE_ONLY_R2:-0}" = "1" ]; then run2 memcheck; run2 synccheck; exit 0; fi
+if [ "${PFB_SANITIZE_ONLY_SIMT:-0}" = "1" ]; then run racecheck "$SIMT"; run memcheck "$SIMT"; exit 0; fi
 run2 memcheck
 run2 synccheck
 run memcheck "$UMMA"
