@@ -372,7 +372,6 @@ class RAFT(BaseModel):
             self._graph_sig = sig
         key = self._graph_key(images, flow_init)
         ent = self._graphs.get(key)
-        dev = images.device
         if ent is None and self.graph_capture_after > 0:
             # a capture costs about four forwards (two warm-ups, the capture, its first replay) and pins the forward's memory:
             # only shapes that come back are captured (infer.py / validate.py feed dataset-dependent sizes, often once each)
@@ -385,7 +384,7 @@ class RAFT(BaseModel):
                     return self._forward_device(images, flow_init), False
         if ent is None:
             with _gate.capture():
-                ent = self._capture(key, images, flow_init)
+                ent = self._graphs.get(key) or self._capture(key, images, flow_init)  # (another thread may have got there first)
         graph, static_in, static_init, flow_up, flow_small, launches = ent[:6]
         with _gate.forward():
             static_in.copy_(images, non_blocking=True)
