@@ -88,3 +88,33 @@ def test_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.LibraryMissing):
         _lib.load()
+
+
+def test_struct_fields_match_the_header():
+    """Field names and order of every struct in include/ptlflow_b200.h equal the ctypes mirrors in ptlflow_b200/_lib.py
+    (a field added on one side only would shift everything behind it silently)."""
+    import re
+
+    from ptlflow_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "ptlflow_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)  # comments out
+    mirrors = {"pfb_conv_src": _lib.ConvSrc, "pfb_conv_params": _lib.ConvParams, "pfb_layer": _lib.Layer, "pfb_raft_cfg": _lib.RaftCfg,
+               "pfb_raft_weights": _lib.RaftWeights, "pfb_raft_buffers": _lib.RaftBuffers}
+    found = 0
+    for body, name in re.findall(r"typedef\s+struct\s*\{(.*?)\}\s*(\w+)\s*;", text, flags=re.S):
+        if name not in mirrors:
+            continue
+        found += 1
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "int a, b, c" / "const void* weight" / "pfb_conv_src src[PFB_MAX_SRC]" / "void* const* pyramid"
+            first, *rest = [d.strip() for d in decl.split(",")]
+            names = [re.sub(r"\[.*\]", "", first.split()[-1]).lstrip("*")] + [re.sub(r"\[.*\]", "", r).lstrip("*").strip() for r in rest]
+            fields += names
+        mirror = [f[0] for f in mirrors[name]._fields_]
+        assert fields == mirror, f"{name}: header {fields} != ctypes {mirror}"
+    assert found == len(mirrors)
